@@ -1,0 +1,326 @@
+/* scope_oracle.c — CPU ORACLE for the scope-accumulation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker, never the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load the library built from it.  The shipped path
+ * (obs-color-monitor_b200/csrc) never links or calls anything in oracle/.
+ *
+ * It restates, in plain C with no libobs, the algorithm of the reference
+ * (norihiro/obs-color-monitor @ e904d82; citations relative to that tree):
+ *
+ *   histogram   src/histogram.c:330-418   (his_calculate_max, his_fix_max_level,
+ *                                          his_draw_histogram)
+ *   waveform    src/waveform.c:201-257    (inc_uint8, wvs_draw_waveform)
+ *   vectorscope src/vectorscope.c:217-238 (vss_draw_vectorscope)
+ *   surface     src/common.h:24-30, src/common.c:352-364 (plane placement)
+ *   fan-out     src/roi.c:329-341         (one surface, every scope in turn)
+ *   transform   data/common.effect:23-43  (PSConvertRGB_YUV601 / 709)
+ *   colourspace src/util.c:25-41          (1 = BT.601, 2 = BT.709)
+ *   display     data/vectorscope.effect:27-33, data/waveform.effect:30-39
+ *
+ * PARITY PIN STATUS
+ *   Integer accumulation (hist / waveform / vectorscope, and the histogram
+ *   post-pass): PINNED — tests/test_oracle_vs_ref.py checks every function here
+ *   bit-for-bit against the reference's own loops, compiled unmodified from
+ *   /root/reference into oracle/_ref/libref.so (oracle/Makefile), and the
+ *   resulting vectors are committed under tests/golden/.
+ *   RGB->YUV transform: PARITY UNPINNED.  In the reference it is a float pixel
+ *   shader whose evaluation order, FMA contraction and float->UNORM8 rounding
+ *   belong to the GPU driver; the reference holds no test or
+ *   vector for it.  The definition below is the one SURVEY.md §8(c) froze.
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+#define NBINS 256
+
+/* mirror of struct cm_surface_data (common.h:24-30) without the texture */
+struct orc_surface {
+	const uint8_t *rgb_data, *yuv_data;
+	uint32_t linesize, width, height;
+	int colorspace;
+};
+
+/* ------------------------------------------------------------------ */
+/* RGB -> YUV, pinned definition:                     */
+/*   xf = (float)X / 255.0f                                            */
+/*   t  = ((c0*rf + c1*gf) + c2*bf) + off      fp32, in this order,     */
+/*        no contraction (build with -ffp-contract=off)                 */
+/*   q  = (uint8_t)floorf(min(max(t,0),1) * 255.0f + 0.5f)              */
+/* coefficients exactly as printed in data/common.effect:27-29,38-40;   */
+/* off = 0.5f - 1.0f/256.0f (U), 0 (Y), 0.5f (V).                       */
+/* Output bytes [U, Y, V, 255] (B<-z, G<-y, R<-x, A<-1).               */
+/* ------------------------------------------------------------------ */
+struct yuv_coeffs {
+	float u[3], y[3], v[3];
+};
+
+static const struct yuv_coeffs k_bt601 = {
+	{-0.147643f, -0.289855f, +0.437500f},
+	{+0.299000f, +0.587000f, +0.114000f},
+	{+0.437500f, -0.366351f, -0.071147f},
+};
+static const struct yuv_coeffs k_bt709 = {
+	{-0.100643f, -0.338571f, +0.439216f},
+	{+0.212600f, +0.715200f, +0.072200f},
+	{+0.439216f, -0.398941f, -0.040273f},
+};
+
+static inline uint8_t quantise_unorm8(float t)
+{
+	t = fminf(fmaxf(t, 0.0f), 1.0f);
+	float s = t * 255.0f;
+	s = s + 0.5f;
+	return (uint8_t)floorf(s);
+}
+
+static inline float dot3_off(const float c[3], float r, float g, float b, float off)
+{
+	float a0 = c[0] * r;
+	float a1 = c[1] * g;
+	float a2 = c[2] * b;
+	float s = a0 + a1;
+	s = s + a2;
+	s = s + off;
+	return s;
+}
+
+ORC_API void orc_rgb_to_yuv_pixel(int colorspace, uint8_t r8, uint8_t g8, uint8_t b8, uint8_t out_uyv[3])
+{
+	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
+	const float r = (float)r8 / 255.0f;
+	const float g = (float)g8 / 255.0f;
+	const float b = (float)b8 / 255.0f;
+	const float off_u = 0.5f - 1.0f / 256.0f;
+	out_uyv[0] = quantise_unorm8(dot3_off(k->u, r, g, b, off_u));
+	out_uyv[1] = quantise_unorm8(dot3_off(k->y, r, g, b, 0.0f));
+	out_uyv[2] = quantise_unorm8(dot3_off(k->v, r, g, b, 0.5f));
+}
+
+/* Whole plane: BGRA in, [U,Y,V,255] out.  Alpha of the source is ignored
+ * (the shader writes a=1, common.effect:30,41). */
+ORC_API void orc_rgb_to_yuv(const uint8_t *bgra, uint32_t linesize, uint32_t width, uint32_t height,
+			    int colorspace, uint8_t *yuv, uint32_t yuv_linesize)
+{
+	for (uint32_t y = 0; y < height; y++) {
+		const uint8_t *s = bgra + (size_t)linesize * y;
+		uint8_t *d = yuv + (size_t)yuv_linesize * y;
+		for (uint32_t x = 0; x < width; x++, s += 4, d += 4) {
+			uint8_t uyv[3];
+			orc_rgb_to_yuv_pixel(colorspace, s[2], s[1], s[0], uyv);
+			d[0] = uyv[0];
+			d[1] = uyv[1];
+			d[2] = uyv[2];
+			d[3] = 255;
+		}
+	}
+}
+
+/* Exhaustive helper for tests: all 2^24 (r,g,b) -> packed u | y<<8 | v<<16,
+ * index = r<<16 | g<<8 | b.  Also reports whether the [0,1] clamp ever
+ * changed a value (it must not: the GPU kernel relies on that). */
+ORC_API int orc_rgb_to_yuv_table(int colorspace, uint32_t *out /* 1<<24 entries */)
+{
+	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
+	const float off_u = 0.5f - 1.0f / 256.0f;
+	int clamp_active = 0;
+	for (uint32_t r8 = 0; r8 < 256; r8++)
+		for (uint32_t g8 = 0; g8 < 256; g8++)
+			for (uint32_t b8 = 0; b8 < 256; b8++) {
+				const float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, b = (float)b8 / 255.0f;
+				const float tu = dot3_off(k->u, r, g, b, off_u);
+				const float ty = dot3_off(k->y, r, g, b, 0.0f);
+				const float tv = dot3_off(k->v, r, g, b, 0.5f);
+				if (tu < 0.0f || tu > 1.0f || ty < 0.0f || ty > 1.0f || tv < 0.0f || tv > 1.0f)
+					clamp_active = 1;
+				out[(r8 << 16) | (g8 << 8) | b8] = (uint32_t)quantise_unorm8(tu) |
+								    ((uint32_t)quantise_unorm8(ty) << 8) |
+								    ((uint32_t)quantise_unorm8(tv) << 16);
+			}
+	return clamp_active;
+}
+
+/* src/util.c:25-41 with the OBS video-info lookup replaced by its default */
+ORC_API int orc_calc_colorspace(int colorspace)
+{
+	if (colorspace == 1 || colorspace == 2)
+		return colorspace;
+	return 2;
+}
+
+/* ------------------------------------------------------------------ */
+/* plane selection shared by histogram and waveform                    */
+/* (histogram.c:367-373, waveform.c:228-234): RGB bits win over YUV.    */
+/* ------------------------------------------------------------------ */
+static const uint8_t *pick_plane(uint32_t components, const struct orc_surface *s)
+{
+	if (components & 0x07)
+		return s->rgb_data;
+	if (components & 0x70)
+		return s->yuv_data;
+	return NULL;
+}
+
+/* ------------------------------------------------------------------ */
+/* histogram: raw counts.  dbuf = 256 x {slot0 R|V, slot1 G|Y, slot2 B|U, 0} */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_histogram_counts(uint32_t components, const struct orc_surface *s, uint32_t dbuf[NBINS * 4])
+{
+	memset(dbuf, 0, sizeof(uint32_t) * NBINS * 4);
+	const uint8_t *plane = pick_plane(components, s);
+	if (!plane)
+		return;
+	const int want_b = (components & 0x11) != 0;
+	const int want_g = (components & 0x22) != 0;
+	const int want_r = (components & 0x44) != 0;
+	for (uint32_t y = 0; y < s->height; y++) {
+		const uint8_t *p = plane + (size_t)s->linesize * y;
+		for (uint32_t x = 0; x < s->width; x++, p += 4) {
+			if (p[3] == 0)
+				continue;
+			if (want_r)
+				dbuf[p[2] * 4 + 0] += 1;
+			if (want_g)
+				dbuf[p[1] * 4 + 1] += 1;
+			if (want_b)
+				dbuf[p[0] * 4 + 2] += 1;
+		}
+	}
+}
+
+/* histogram post-pass (histogram.c:330-355, 397-417): hi_max then in-place
+ * u32 -> float (linear) or log-normalised float. */
+ORC_API void orc_histogram_post(uint32_t components, uint32_t width, uint32_t height, int level_fixed_value,
+				int level_ratio_value, int logscale, const uint32_t dbuf[NBINS * 4],
+				float out[NBINS * 4], uint32_t hi_max[3])
+{
+	if (level_fixed_value > 0) {
+		uint32_t v = (uint32_t)level_fixed_value;
+		hi_max[0] = hi_max[1] = hi_max[2] = v ? v : 1;
+	} else if (level_ratio_value > 0) {
+		uint32_t v = (uint32_t)((uint64_t)width * height * (uint64_t)level_ratio_value / 1000);
+		hi_max[0] = hi_max[1] = hi_max[2] = v ? v : 1;
+	} else {
+		static const uint32_t mask[3] = {0x44, 0x22, 0x11};
+		for (int j = 0; j < 3; j++) {
+			uint32_t m = 1;
+			if (components & mask[j])
+				for (int i = 0; i < NBINS; i++)
+					if (dbuf[i * 4 + j] > m)
+						m = dbuf[i * 4 + j];
+			hi_max[j] = m;
+		}
+	}
+
+	if (logscale) {
+		/* untouched slots keep the integer bit pattern (in-place reinterpretation
+		 * in the reference: only enabled channels are rewritten, histogram.c:405-413) */
+		memcpy(out, dbuf, sizeof(uint32_t) * NBINS * 4);
+		static const uint32_t mask[3] = {0x44, 0x22, 0x11};
+		for (int j = 0; j < 3; j++) {
+			if (!(components & mask[j]))
+				continue;
+			const float scale = 1.0f / logf((float)(hi_max[j] + 1));
+			for (int i = 0; i < NBINS; i++) {
+				const uint32_t c = dbuf[i * 4 + j];
+				out[i * 4 + j] = c ? logf((float)(c + 1)) * scale : 0;
+			}
+			hi_max[j] = 1;
+		}
+	} else {
+		for (int i = 0; i < NBINS * 4; i++)
+			out[i] = (float)dbuf[i];
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* waveform: dbuf = u8 [256][width][4], row 0 = value 255, byte 3 = 0   */
+/* ------------------------------------------------------------------ */
+static inline void sat_inc(uint8_t *c)
+{
+	if (*c != 255)
+		*c += 1;
+}
+
+ORC_API void orc_waveform(uint32_t components, const struct orc_surface *s, uint8_t *dbuf)
+{
+	const size_t row = (size_t)s->width * 4;
+	memset(dbuf, 0, row * NBINS);
+	const uint8_t *plane = pick_plane(components, s);
+	if (!plane)
+		return;
+	const int want_b = (components & 0x11) != 0;
+	const int want_g = (components & 0x22) != 0;
+	const int want_r = (components & 0x44) != 0;
+	for (uint32_t y = 0; y < s->height; y++) {
+		const uint8_t *p = plane + (size_t)s->linesize * y;
+		for (uint32_t x = 0; x < s->width; x++, p += 4) {
+			if (p[3] == 0)
+				continue;
+			uint8_t *col = dbuf + (size_t)x * 4;
+			if (want_b)
+				sat_inc(col + (size_t)(NBINS - 1 - p[0]) * row + 0);
+			if (want_g)
+				sat_inc(col + (size_t)(NBINS - 1 - p[1]) * row + 1);
+			if (want_r)
+				sat_inc(col + (size_t)(NBINS - 1 - p[2]) * row + 2);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* vectorscope: dbuf = u8 [256][256], row = 255 - V, column = U; no     */
+/* alpha test; reads the YUV plane only.                                */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_vectorscope(const struct orc_surface *s, uint8_t dbuf[NBINS * NBINS])
+{
+	memset(dbuf, 0, NBINS * NBINS);
+	if (!s->yuv_data)
+		return;
+	for (uint32_t y = 0; y < s->height; y++) {
+		const uint8_t *p = s->yuv_data + (size_t)s->linesize * y;
+		for (uint32_t x = 0; x < s->width; x++, p += 4)
+			sat_inc(dbuf + p[0] + NBINS * (255 - p[2]));
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* ROI fan-out (roi.c:329-341): the same surface goes to every          */
+/* registered scope one after the other.  mask bit0 hist, bit1 wave,    */
+/* bit2 vectorscope; NULL outputs are skipped.                          */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_fanout(const struct orc_surface *s, uint32_t hist_components, uint32_t wave_components,
+			uint32_t *hist_dbuf, uint8_t *wave_dbuf, uint8_t *vscope_dbuf)
+{
+	if (vscope_dbuf)
+		orc_vectorscope(s, vscope_dbuf);
+	if (wave_dbuf)
+		orc_waveform(wave_components, s, wave_dbuf);
+	if (hist_dbuf)
+		orc_histogram_counts(hist_components, s, hist_dbuf);
+}
+
+/* ------------------------------------------------------------------ */
+/* display mapping of an 8-bit bin image (vectorscope.effect:30-31,      */
+/* waveform.effect:33-36): r = (c/255) * intensity, clamped to 1, then   */
+/* stored as UNORM8 with the same rounding rule as the transform.        */
+/* PARITY UNPINNED (shader + ROP), definition from SURVEY.md §8(d) cfg 3. */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_apply_intensity(const uint8_t *bins, size_t n, int intensity, uint8_t *out)
+{
+	if (intensity < 1)
+		intensity = 1;
+	const float k = (float)intensity;
+	for (size_t i = 0; i < n; i++) {
+		float r = (float)bins[i] / 255.0f;
+		r = r * k;
+		if (r > 1.0f)
+			r = 1.0f;
+		float q = r * 255.0f;
+		q = q + 0.5f;
+		out[i] = (uint8_t)floorf(q);
+	}
+}
