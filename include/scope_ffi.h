@@ -1,0 +1,191 @@
+/* scope_ffi.h — C-ABI of libscope_b200.so: the B200 (sm_100a) implementation of
+ * obs-color-monitor's per-pixel scope accumulation path.
+ *
+ * This is the drop-in boundary.  Plain C types only: pointers, sizes, PODs.
+ * Every entry point returns an int status (SCOPE_OK == 0) and never falls back
+ * to a CPU implementation: if no CUDA device / kernel image is usable the call
+ * fails loudly with SCOPE_ERR_NO_DEVICE or SCOPE_ERR_CUDA.
+ *
+ * Reference interfaces replaced (citations relative to the reference tree,
+ * norihiro/obs-color-monitor @ e904d82):
+ *
+ *   struct scope_surface          <- struct cm_surface_data        src/common.h:24-30
+ *   scope_accumulate_host()       <- the bodies of his_surface_cb  src/histogram.c:432-450
+ *                                    (his_draw_histogram           src/histogram.c:357-418),
+ *                                    wvs_surface_cb                src/waveform.c:272-289
+ *                                    (wvs_draw_waveform            src/waveform.c:220-257),
+ *                                    vss_surface_cb                src/vectorscope.c:248-265
+ *                                    (vss_draw_vectorscope         src/vectorscope.c:217-238),
+ *                                    called once per surface instead of once per scope:
+ *                                    the fan-out of roi_surface_cb src/roi.c:329-341
+ *   SCOPE_MODE_FUSED transform    <- PSConvertRGB_YUV601/709       data/common.effect:23-43
+ *                                    (+ render_rgb_yuv             src/common.c:170-221)
+ *   scope_submit_host()/scope_wait_host()
+ *                                 <- the 3-deep stagesurface ring  src/common.h:46,
+ *                                    src/common.c:260-268,316-329,375-403
+ *   scope_params.colorspace       <- calc_colorspace               src/util.c:25-41
+ *   hist post-pass fields         <- his_calculate_max / his_fix_max_level / float+log
+ *                                    conversion                    src/histogram.c:330-355,397-417
+ *   *_intensity / *_display       <- PSDrawBare / PSDrawOverlay    data/vectorscope.effect:27-33,
+ *                                                                  data/waveform.effect:30-39
+ *
+ * Output layouts are byte-for-byte the reference's tex_buf layouts:
+ *   histogram    uint32[256][4]   slot 0 = R|V, 1 = G|Y, 2 = B|U, 3 = 0       (histogram.c:379-395)
+ *   waveform     uint8 [256][W][4] row 0 = value 255, bytes B|U,G|Y,R|V,0, saturating at 255
+ *                                                                             (waveform.c:240-256)
+ *   vectorscope  uint8 [256][256] row = 255 - V, column = U, saturating at 255 (vectorscope.c:226-237)
+ */
+#ifndef SCOPE_FFI_H
+#define SCOPE_FFI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCOPE_ABI_VERSION 1
+
+enum scope_status {
+	SCOPE_OK = 0,
+	SCOPE_ERR_INVALID = 1,     /* bad argument (NULL plane that the request needs, zero width, ...) */
+	SCOPE_ERR_NO_DEVICE = 2,   /* no CUDA device / driver: there is NO CPU fallback */
+	SCOPE_ERR_CUDA = 3,        /* a CUDA call failed; see scope_last_error() */
+	SCOPE_ERR_UNSUPPORTED = 4, /* geometry outside what the kernels handle (height > 65535, ...) */
+	SCOPE_ERR_NOMEM = 5,
+	SCOPE_ERR_BUSY = 6,        /* ring slot still in flight (the caller drops the frame, common.c:260-268) */
+};
+
+/* which scopes to accumulate (bit mask) */
+#define SCOPE_HIST 0x1u
+#define SCOPE_WAVE 0x2u
+#define SCOPE_VSCOPE 0x4u
+#define SCOPE_ALL 0x7u
+
+/* `components` masks, identical to the reference (histogram.c:27-30, waveform.c:26-29) */
+#define SCOPE_COMP_RGB 0x07u
+#define SCOPE_COMP_Y 0x20u
+#define SCOPE_COMP_UV 0x50u
+#define SCOPE_COMP_YUV 0x70u
+
+/* where the YUV plane comes from */
+#define SCOPE_MODE_FUSED 0   /* only rgb_data is read; BT.601/709 transform applied in registers */
+#define SCOPE_MODE_SURFACE 1 /* rgb_data / yuv_data are used exactly as the reference's callbacks
+                                use them (integer-only path, no transform) */
+
+/* mirror of struct cm_surface_data (common.h:24-30); host OR device pointers
+ * depending on the entry point */
+struct scope_surface {
+	const uint8_t *rgb_data; /* BGRA, may be NULL if no requested scope reads it */
+	const uint8_t *yuv_data; /* [U,Y,V,A] bytes; ignored in SCOPE_MODE_FUSED */
+	uint32_t linesize;       /* bytes between rows (>= width*4) */
+	uint32_t width, height;
+	int32_t colorspace;      /* 1 = BT.601, 2 = BT.709 (anything else: 709, util.c:25-41) */
+};
+
+struct scope_params {
+	uint32_t scopes;          /* SCOPE_HIST | SCOPE_WAVE | SCOPE_VSCOPE */
+	uint32_t mode;            /* SCOPE_MODE_FUSED | SCOPE_MODE_SURFACE */
+	uint32_t hist_components; /* his_source.components */
+	uint32_t wave_components; /* wvs_source.components */
+	/* histogram post-pass (histogram.c:397-417) */
+	int32_t level_fixed_value;
+	int32_t level_ratio_value;
+	int32_t logscale;
+	/* display mapping; 0 = not requested */
+	int32_t wave_intensity;
+	int32_t vscope_intensity;
+	uint32_t reserved[3];
+};
+
+/* host result buffers; NULL members are skipped */
+struct scope_out_host {
+	uint32_t *hist_counts;   /* [1024] raw counts */
+	float *hist_float;       /* [1024] what the reference uploads as GS_RGBA32F (linear or log) */
+	uint32_t *hist_max;      /* [3]    hi_max after the post-pass */
+	uint8_t *wave;           /* [256*width*4] */
+	uint8_t *vscope;         /* [65536] */
+	uint8_t *wave_display;   /* [256*width*4] intensity applied (needs wave_intensity > 0) */
+	uint8_t *vscope_display; /* [65536]       intensity applied (needs vscope_intensity > 0) */
+};
+
+/* device result buffers for the batched entry point; per frame f the arrays are
+ * at base + f * stride (strides in ELEMENTS of the array type; 0 = densely packed) */
+struct scope_out_device {
+	uint32_t *hist_counts; /* [n][1024]          */
+	uint32_t *hist_max;    /* [n][4] (3 used)    */
+	uint8_t *wave;         /* [n][256*width*4]   */
+	uint8_t *vscope;       /* [n][65536]         */
+	uint8_t *vscope_display;
+	uint8_t *wave_display;
+};
+
+/* partial (unclamped) accumulators for tile-sharded frames: sums over tiles /
+ * GPUs are formed on these (e.g. NCCL all-reduce as int32), then
+ * scope_finalize_partial() applies the saturation the reference applies per
+ * increment.  min(sum of partials, 255) == the reference's saturating count. */
+struct scope_partial_device {
+	uint32_t *hist_counts; /* [1024]            additive */
+	uint32_t *wave_pairs;  /* [256][width][2]   u16x4 per (level, column): B,G | R,0 ; additive
+	                                            as int32 lanes while every u16 stays < 65536 */
+	uint32_t *vscope_counts; /* [65536]         additive */
+};
+
+typedef struct scope_ctx scope_ctx;
+
+int scope_abi_version(void);
+
+/* device < 0: current device.  Fails with SCOPE_ERR_NO_DEVICE when there is no GPU. */
+int scope_ctx_create(int device, scope_ctx **out_ctx);
+void scope_ctx_destroy(scope_ctx *ctx);
+const char *scope_last_error(const scope_ctx *ctx); /* ctx may be NULL: last create error */
+
+/* number of kernel launches issued through this context so far */
+uint64_t scope_launch_count(const scope_ctx *ctx);
+/* SM count of the context's device (grid sizing), 0 on error */
+int scope_sm_count(const scope_ctx *ctx);
+
+/* ---- host buffers in, host buffers out: the drop-in for the surface callbacks ----
+ * Synchronous.  surface pointers are HOST memory, valid only during the call
+ * (exactly like the mapped stagesurface, common.c:343-372). */
+int scope_accumulate_host(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
+			  const struct scope_out_host *out);
+
+/* ---- 3-deep ring (CM_SURFACE_QUEUE_SIZE, common.h:46) for streams ----
+ * scope_submit_host copies the surface into pinned staging slot `slot` (0..2) and
+ * enqueues H2D + kernels + D2H on that slot's stream, returning before the GPU
+ * finishes; SCOPE_ERR_BUSY if the slot is still in flight (caller drops the frame).
+ * scope_wait_host blocks until the slot's results are in `out`. */
+#define SCOPE_RING_SLOTS 3
+int scope_submit_host(scope_ctx *ctx, int slot, const struct scope_params *params,
+		      const struct scope_surface *surface);
+int scope_wait_host(scope_ctx *ctx, int slot, const struct scope_out_host *out);
+
+/* ---- device buffers in, device buffers out, batched ----
+ * surface pointers are DEVICE memory; frame f lives at pointer + f*frame_stride
+ * bytes.  Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream). */
+int scope_accumulate_device(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
+			    uint32_t n_frames, size_t frame_stride, const struct scope_out_device *out, void *stream);
+
+/* ---- tile-sharded frames (ROI tiles / row bands across GPUs) ----
+ * Accumulates ONE tile (surface = the tile's rows; `x_offset` = first column of
+ * the tile inside the full-width accumulators, full_width = their width) into
+ * caller-zeroed partial accumulators.  Asynchronous on `stream`. */
+int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *tile,
+			     uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
+			     void *stream);
+/* clamp the (summed) partials into the reference layouts */
+int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *params, uint32_t full_width,
+			   uint32_t full_height, const struct scope_partial_device *partial,
+			   const struct scope_out_device *out, void *stream);
+
+/* size helpers */
+size_t scope_wave_bytes(uint32_t width);          /* 256*width*4 */
+size_t scope_partial_wave_words(uint32_t width);  /* 256*width*2 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCOPE_FFI_H */
