@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the fused histogram+waveform+vectorscope pass on 3840x2160 BGRA.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU loops)
+
+One step = one pass of the hot path over one batch of synthetic frames (default: the
+64-frame mixed batch of BASELINE config 5 per GPU, 2.1 GB, larger than 2x L2 so every pass
+streams from HBM).  Prints ONE JSON line (rank 0).
+
+  value     whole-job frames/s with the batch already resident in HBM, timed with CUDA events
+            on the launch stream, max over ranks
+  e2e       frames/s through the host-buffer C-ABI (scope_submit_host / scope_wait_host ring):
+            pinned host frames in, host results out, H2D and D2H copies inside the timed region
+  roofline  the accumulation kernel alone: algorithmic bytes (W*H*4 per frame) / its CUDA-event
+            duration (scope_profile_*), against MEASURED_PEAKS.json's hbm_gbs
+  cpu_baseline  the reference's own loops (oracle/_ref) on the box's host cores, bounded sample
+
+Under torchrun (N > 1) every rank owns one GPU and a disjoint share of the frames
+(frame-sharded, no data-path collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH_4K, HEIGHT_4K = 3840, 2160
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=64)
+    ap.add_argument("--width", type=int, default=WIDTH_4K)
+    ap.add_argument("--height", type=int, default=HEIGHT_4K)
+    ap.add_argument("--content", default="mixed", choices=["mixed", "random", "natural", "ramp", "solid"])
+    ap.add_argument("--colorspace", type=int, default=2)
+    ap.add_argument("--e2e-frames", type=int, default=16, help="frames per step on the host-buffer path")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = one frame per host thread (bounded)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/_ref when present, else the oracle port)
+# --------------------------------------------------------------------------------------
+class CpuReference:
+    """The reference's three draw loops (hist RGB + waveform RGB + vectorscope) on host threads,
+    one frame per thread at a time: oracle/_ref (the reference's own compiled loops) when it
+    exists, else the oracle port.  The YUV plane (made by the GPU shader in the reference) is
+    prepared once, outside every timed region."""
+
+    def __init__(self, width, height, n_frames, threads, colorspace, content):
+        import obs_color_monitor_b200 as pkg
+        from oracle.oracle import Oracle, Ref
+
+        self.orc = Oracle()
+        self.kind = "reference" if Ref.available() else "port"
+        self.impl = Ref() if self.kind == "reference" else None
+        self.threads, self.n = threads, n_frames
+        offset = {"mixed": None, "random": 0, "ramp": 1, "solid": 2, "natural": 3}[content]
+        self.frames = []
+        for i in range(n_frames):
+            f = pkg.frames.mixed(width, height, i if offset is None else 4 * i + offset)
+            self.frames.append((f, self.orc.rgb_to_yuv(f, colorspace)))
+
+    def _work(self, i):
+        f, yuv = self.frames[i % self.n]
+        if self.impl is not None:
+            self.impl.histogram(0x07, f, yuv)
+            self.impl.waveform(0x07, f, yuv)
+            self.impl.vectorscope(yuv)
+        else:
+            self.orc.histogram_counts(0x07, f, yuv)
+            self.orc.waveform(0x07, f, yuv)
+            self.orc.vectorscope(yuv)
+
+    def step(self):
+        """one pass over the sample; returns seconds"""
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=self.threads) as ex:
+            t0 = time.perf_counter()
+            list(ex.map(self._work, range(self.n)))
+            return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_sample_frames or min(threads, 32)
+    ref = CpuReference(args.width, args.height, n, threads, args.colorspace, args.content)
+    budget_s, spent, times = 150.0, 0.0, []
+    warm = 0
+    for _ in range(args.warmup):
+        spent += ref.step()
+        warm += 1
+        if spent > budget_s / 3:
+            break
+    for _ in range(args.steps):
+        dt = ref.step()
+        times.append(dt)
+        spent += dt
+        if spent > budget_s:
+            break
+    value = n * len(times) / sum(times)
+    sample = (f"{n} {args.content} {args.width}x{args.height} frames per step, the reference's hist RGB + waveform RGB "
+              f"+ vectorscope loops, one frame per thread over {threads} threads, YUV plane precomputed")
+    line = {
+        "impl": "reference", "metric": "frames/sec fused scopes @3840x2160 BGRA", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_step": n, "width": args.width, "height": args.height},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": ref.kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"batch of {args.frames_per_gpu} independent {args.width}x{args.height} BGRA frames per GPU "
+            f"({args.content}: random/ramp/solid/natural cycle), fused histogram RGB + waveform RGB + "
+            f"vectorscope BT.{'601' if args.colorspace == 1 else '709'}, frame-sharded (BASELINE config 5; "
+            f"metric quoted @3840x2160)")
+
+
+# --------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import obs_color_monitor_b200 as pkg
+    from obs_color_monitor_b200 import frames_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the scope kernels have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H, n = args.width, args.height, args.frames_per_gpu
+
+    eng = pkg.ScopeEngine(local_rank)
+    st = pkg.ScopeSettings(colorspace=args.colorspace)
+    batch = frames_torch.mixed_batch(n, W, H, dev, first_index=rank * n, content=args.content)
+    out = eng.alloc_device_out(n, W, st, dev)
+    torch.cuda.synchronize()
+
+    def step():
+        eng.accumulate_device(batch, settings=st, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # sanity: every pixel of every frame was counted (alpha is 255 everywhere in the synthetic batch)
+    hsum = out["hist"].to(torch.int64).sum(dim=1)
+    assert bool((hsum == 3 * W * H).all()), "histogram totals are wrong"
+    assert bool((out["vscope"].amax(dim=(1, 2)) > 0).all())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    eng.ctx.profile_enable(True)
+    eng.ctx.profile_read()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    kernel_ms = eng.ctx.profile_read()
+    eng.ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    total_frames = n * world * args.steps
+    value = total_frames / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the accumulation kernel (rank-local, then max duration over ranks) ----
+    k_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+    kt = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    k_ms = float(kt.item())
+    launches_per_step = max(len(kernel_ms) // max(args.steps, 1), 1)
+    alg_bytes_per_launch = n * W * H * 4 / launches_per_step
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy, read+write)"
+    except Exception:
+        pass
+    achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "scope_strip_kernel<SRC_RGB,VSCOPE,fused,TMA>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
+                "kernel_share_of_step": (k_ms * launches_per_step) / (elapsed_ms / args.steps)}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        roofline["traffic_note"] = tr.get("note")
+    except Exception:
+        pass
+
+    # ---- e2e: host buffers through the C-ABI ring, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, eng, st, batch, dev, world, rank)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ns = args.cpu_sample_frames or min(threads, 32)
+        ref = CpuReference(W, H, ns, threads, args.colorspace, args.content)
+        ref.step()
+        dt = ref.step()
+        cpu = {"value": ns / dt, "unit": "frames/s", "cores": threads, "kind": ref.kind,
+               "sample": f"{ns} {args.content} {W}x{H} frames, the reference's hist RGB + waveform RGB + vectorscope "
+                         f"loops, one frame per thread over {threads} threads, {dt:.1f} s, YUV plane precomputed"}
+
+    if rank == 0:
+        line = {
+            "metric": "frames/sec fused scopes @3840x2160 BGRA", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (fp32 colour transform)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "frames_per_gpu": n, "global_batch": n * world,
+                       "width": W, "height": H, "parallelism": f"frame-sharded x{world}",
+                       "l2": "inputs larger than L2 (batch = %.2f GB per GPU per step)" % (n * W * H * 4 / 1e9)},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def run_e2e(args, eng, st, batch, dev, world, rank):
+    """Pinned host frames -> scope_submit_host (H2D + kernels + D2H on the slot's stream) ->
+    scope_wait_host, three slots in flight like the reference's 3-deep stagesurface ring."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import obs_color_monitor_b200 as pkg
+
+    W, H = args.width, args.height
+    nf = min(args.e2e_frames, batch.shape[0])
+    fbytes = W * H * 4
+    lib = eng.lib
+    ptr = lib.scope_host_alloc(nf * fbytes)
+    if not ptr:
+        return None
+    host = np.ctypeslib.as_array((C.c_uint8 * (nf * fbytes)).from_address(ptr)).reshape(nf, H, W, 4)
+    host[:] = batch[:nf].cpu().numpy()
+    wave_bytes = 256 * W * 4
+    res_ptr = lib.scope_host_alloc(3 * (4096 + 12 + 65536 + wave_bytes))
+    slots = pkg._ffi.RING_SLOTS
+    outs = []
+    for s in range(slots):
+        base = res_ptr + s * (4096 + 12 + 65536 + wave_bytes)
+        o = pkg._ffi.OutHost()
+        o.hist_counts, o.hist_max, o.vscope, o.wave = base, base + 4096, base + 4096 + 12, base + 4096 + 12 + 65536
+        outs.append(o)
+    p = st.to_c()
+
+    def surface(i):
+        s = pkg._ffi.Surface()
+        s.rgb_data = ptr + i * fbytes
+        s.yuv_data = None
+        s.linesize, s.width, s.height, s.colorspace = W * 4, W, H, st.colorspace
+        return s
+
+    surfs = [surface(i) for i in range(nf)]
+
+    def step():
+        for i in range(nf):
+            sl = i % slots
+            if i >= slots:
+                eng.ctx.check(lib.scope_wait_host(eng.ctx.handle, sl, C.byref(outs[sl])))
+            eng.ctx.check(lib.scope_submit_host(eng.ctx.handle, sl, C.byref(p), C.byref(surfs[i])))
+        for i in range(max(nf - slots, 0), nf):
+            eng.ctx.check(lib.scope_wait_host(eng.ctx.handle, i % slots, C.byref(outs[i % slots])))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    hist = np.ctypeslib.as_array((C.c_uint32 * 1024).from_address(res_ptr))
+    assert int(hist.sum()) == 3 * W * H, "e2e histogram total is wrong"
+    lib.scope_host_free(ptr)
+    lib.scope_host_free(res_ptr)
+    return {"value": nf * world * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": nf * fbytes,
+            "d2h_bytes_per_step": nf * (4096 + 16 + 65536 + wave_bytes), "frames_per_step": nf,
+            "path": "scope_submit_host/scope_wait_host, 3-slot ring, pinned host frames, wall clock max over ranks"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,22 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *params, ui
 			   uint32_t full_height, const struct scope_partial_device *partial,
 			   const struct scope_out_device *out, void *stream);
 
+/* Per-launch device timing of the accumulation kernel (CUDA events recorded on the launch
+ * stream around each launch while enabled).  scope_profile_read waits for the recorded
+ * launches, writes their durations in milliseconds (oldest first) and forgets them; returns
+ * how many were written. */
+int scope_profile_enable(scope_ctx *ctx, int on);
+int scope_profile_read(scope_ctx *ctx, float *ms_out, int max_entries);
+
+/* page-locked host memory (what a caller should hand to the host entry points for
+ * full PCIe speed; pageable pointers work too, just slower).  NULL on failure. */
+void *scope_host_alloc(size_t bytes);
+void scope_host_free(void *p);
+
+/* test hook, not part of the drop-in surface: the kernels' own RGB->YUV transform for
+ * all 2^24 colours, d_out[r<<16|g<<8|b] = u | y<<8 | v<<16 (device pointer). */
+int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
+
 /* size helpers */
 size_t scope_wave_bytes(uint32_t width);          /* 256*width*4 */
 size_t scope_partial_wave_words(uint32_t width);  /* 256*width*2 */

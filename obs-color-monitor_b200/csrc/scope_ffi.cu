@@ -1,0 +1,997 @@
+// scope_ffi.cu — host side of libscope_b200.so: the C-ABI declared in include/scope_ffi.h.
+//
+// Replaces, behind the reference's cm_surface_cb_t seam (src/common.h:32), the work of
+// his_surface_cb / wvs_surface_cb / vss_surface_cb (src/histogram.c:432-450,
+// src/waveform.c:272-289, src/vectorscope.c:248-265) and of the RGB->YUV shader pass
+// (src/common.c:170-221, data/common.effect).  There is no CPU fallback in here.
+#include "scope_kernels.cuh"
+#include "../../include/scope_ffi.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+using namespace scope;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+				    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+				    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct RingSlot {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	bool in_flight = false;
+	// device staging for the host entry points
+	uint8_t *d_in = nullptr;
+	size_t d_in_bytes = 0;
+	uint32_t *d_hist = nullptr;    // 1024
+	uint32_t *d_hist_max = nullptr; // 4
+	uint8_t *d_wave = nullptr;
+	uint8_t *d_wave_disp = nullptr;
+	size_t d_wave_bytes = 0;
+	uint8_t *d_vscope = nullptr;      // 65536
+	uint8_t *d_vscope_disp = nullptr; // 65536
+	// pinned result staging
+	uint8_t *h_res = nullptr;
+	size_t h_res_bytes = 0;
+	// what the in-flight submission asked for
+	scope_params params{};
+	uint32_t width = 0, height = 0;
+};
+
+} // namespace
+
+struct scope_ctx {
+	int device = 0;
+	int sm_count = 0;
+	std::string err;
+	uint64_t launches = 0;
+	PFN_encodeTiled encode = nullptr;
+	// scratch u32 vectorscope accumulators [n][65536]
+	uint32_t *d_vs_acc = nullptr;
+	size_t vs_acc_frames = 0;
+	uint32_t *d_hist_scratch = nullptr;
+	size_t hist_scratch_frames = 0;
+	RingSlot ring[SCOPE_RING_SLOTS];
+	std::mutex mu;
+	// optional per-launch timing of the strip kernel (scope_profile_*)
+	bool profiling = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+};
+
+namespace {
+
+int fail(scope_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+	char buf[512];
+	if (e != cudaSuccess)
+		snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+	else
+		snprintf(buf, sizeof buf, "%s", what);
+	if (ctx)
+		ctx->err = buf;
+	else
+		g_create_error = buf;
+	return code;
+}
+
+#define CU_TRY(ctx, call)                                              \
+	do {                                                           \
+		cudaError_t e_ = (call);                               \
+		if (e_ != cudaSuccess)                                 \
+			return fail(ctx, SCOPE_ERR_CUDA, #call, e_);   \
+	} while (0)
+
+Coef coef_for(int colorspace)
+{
+	// data/common.effect:27-29 (601) and :38-40 (709); anything but 1 means 709 (util.c:25-41)
+	if (colorspace == 1)
+		return Coef{-0.147643f, -0.289855f, +0.437500f, +0.299000f, +0.587000f,
+			    +0.114000f, +0.437500f, -0.366351f, -0.071147f};
+	return Coef{-0.100643f, -0.338571f, +0.439216f, +0.212600f, +0.715200f,
+		    +0.072200f, +0.439216f, -0.398941f, -0.040273f};
+}
+
+// components -> (source plane, channel mask) exactly like histogram.c:367-377 / waveform.c:228-238
+void decode_components(uint32_t comp, int &src, uint32_t &mask)
+{
+	if (comp & 0x07u)
+		src = SRC_RGB;
+	else if (comp & 0x70u)
+		src = SRC_YUV;
+	else
+		src = SRC_NONE;
+	mask = ((comp & 0x11u) ? 1u : 0u) | ((comp & 0x22u) ? 2u : 0u) | ((comp & 0x44u) ? 4u : 0u);
+	if (src == SRC_NONE)
+		mask = 0;
+}
+
+typedef void (*StripKernel)(const StripParams, const CUtensorMap, const CUtensorMap);
+
+template <int SRC, bool VS, bool SURF, bool TMA>
+void kernel_entry(StripKernel &fn, int &smem)
+{
+	fn = scope_strip_kernel<SRC, VS, SURF, TMA>;
+	smem = SmemLayout<SRC, VS, SURF, TMA>::kTotal;
+}
+
+template <bool SURF, bool TMA>
+bool pick_kernel2(int src, bool vs, StripKernel &fn, int &smem)
+{
+	if (src == SRC_NONE && vs)
+		kernel_entry<SRC_NONE, true, SURF, TMA>(fn, smem);
+	else if (src == SRC_RGB && vs)
+		kernel_entry<SRC_RGB, true, SURF, TMA>(fn, smem);
+	else if (src == SRC_RGB && !vs)
+		kernel_entry<SRC_RGB, false, SURF, TMA>(fn, smem);
+	else if (src == SRC_YUV && vs)
+		kernel_entry<SRC_YUV, true, SURF, TMA>(fn, smem);
+	else if (src == SRC_YUV && !vs)
+		kernel_entry<SRC_YUV, false, SURF, TMA>(fn, smem);
+	else
+		return false;
+	return true;
+}
+
+bool pick_kernel(int src, bool vs, bool surface, bool tma, StripKernel &fn, int &smem)
+{
+	if (surface)
+		return tma ? pick_kernel2<true, true>(src, vs, fn, smem) : pick_kernel2<true, false>(src, vs, fn, smem);
+	return tma ? pick_kernel2<false, true>(src, vs, fn, smem) : pick_kernel2<false, false>(src, vs, fn, smem);
+}
+
+int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x_extent_px, uint32_t linesize,
+	     uint32_t height, uint32_t n_frames, size_t frame_stride)
+{
+	cuuint64_t dims[3] = {x_extent_px, height, n_frames};
+	cuuint64_t strides[2] = {linesize, n_frames > 1 ? (cuuint64_t)frame_stride
+							  : (cuuint64_t)(((size_t)linesize * height + 15) & ~(size_t)15)};
+	cuuint32_t box[3] = {(cuuint32_t)kStripPx, (cuuint32_t)kTileRows, 1};
+	cuuint32_t estr[3] = {1, 1, 1};
+	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base16, dims, strides, box, estr,
+				 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+				 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		char buf[128];
+		snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+		return fail(ctx, SCOPE_ERR_CUDA, buf);
+	}
+	return SCOPE_OK;
+}
+
+struct Request {
+	const uint8_t *rgb, *yuv; // device
+	uint32_t linesize, width, height, n_frames;
+	size_t frame_stride;
+	int colorspace;
+	bool surface;
+	// which column bins / vectorscope this launch serves
+	int src;
+	uint32_t bins_mask, hist_mask, wave_mask;
+	bool vscope;
+	// outputs
+	uint32_t *hist;
+	size_t hist_stride;
+	uint8_t *wave;
+	size_t wave_stride;
+	uint32_t *wave_pairs;
+	uint32_t x_offset, out_width;
+	bool partial;
+	uint32_t *vs_acc;
+	size_t vs_stride;
+};
+
+int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
+{
+	if (rq.src == SRC_NONE && !rq.vscope)
+		return SCOPE_OK;
+	const bool need_rgb = !rq.surface || rq.src == SRC_RGB;
+	const bool need_yuv = rq.surface && (rq.src == SRC_YUV || rq.vscope);
+	if ((need_rgb && !rq.rgb) || (need_yuv && !rq.yuv))
+		return fail(ctx, SCOPE_ERR_INVALID, "a plane the request needs is NULL");
+	if (rq.height > 65535u)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "height > 65535 (u16 column bins)");
+	if ((rq.linesize & 3u) || ((uintptr_t)rq.rgb & 3u) || ((uintptr_t)rq.yuv & 3u) || (rq.frame_stride & 3u))
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "planes must be 4-byte aligned with a 4-byte multiple pitch");
+
+	StripParams P{};
+	P.rgb = rq.rgb;
+	P.yuv = rq.yuv;
+	P.frame_stride = rq.frame_stride;
+	P.linesize = rq.linesize;
+	P.width = rq.width;
+	P.height = rq.height;
+	P.n_frames = rq.n_frames;
+	P.strips = (rq.width + kStripPx - 1) / kStripPx;
+	P.items = P.strips * rq.n_frames;
+	P.bins_mask = rq.bins_mask;
+	P.hist_mask = rq.hist_mask;
+	P.wave_mask = rq.wave_mask;
+	P.x_offset = rq.x_offset;
+	P.out_width = rq.out_width;
+	P.partial = rq.partial ? 1u : 0u;
+	P.hist = rq.hist;
+	P.hist_stride = rq.hist_stride;
+	P.wave = rq.wave;
+	P.wave_stride = rq.wave_stride;
+	P.wave_pairs = rq.wave_pairs;
+	P.vscope_acc = rq.vs_acc;
+	P.vscope_stride = rq.vs_stride;
+	P.coef = coef_for(rq.colorspace);
+
+	// TMA needs 16-byte pitches; the base may be 4-byte aligned (handled by an x offset)
+	const bool strides_ok = (rq.linesize % 16u) == 0 && (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0);
+	const bool same_mis = !(need_rgb && need_yuv) || (((uintptr_t)rq.rgb & 15u) == ((uintptr_t)rq.yuv & 15u));
+	// SCOPE_DISABLE_TMA=1 forces the plain-load kernels (debugging / A-B measurements)
+	const char *no_tma = getenv("SCOPE_DISABLE_TMA");
+	const bool use_tma = ctx->encode != nullptr && strides_ok && same_mis && !(no_tma && no_tma[0] == '1');
+
+	CUtensorMap map_rgb, map_yuv;
+	memset(&map_rgb, 0, sizeof map_rgb);
+	memset(&map_yuv, 0, sizeof map_yuv);
+	if (use_tma) {
+		const uint8_t *any = need_rgb ? rq.rgb : rq.yuv;
+		const uint32_t mis_px = (uint32_t)(((uintptr_t)any & 15u) / 4u);
+		P.tma_x0 = mis_px;
+		if (need_rgb) {
+			int r = make_map(ctx, &map_rgb, rq.rgb - mis_px * 4, mis_px + rq.width, rq.linesize, rq.height,
+					 rq.n_frames, rq.frame_stride);
+			if (r)
+				return r;
+		}
+		if (need_yuv) {
+			int r = make_map(ctx, &map_yuv, rq.yuv - mis_px * 4, mis_px + rq.width, rq.linesize, rq.height,
+					 rq.n_frames, rq.frame_stride);
+			if (r)
+				return r;
+		}
+	}
+
+	StripKernel fn = nullptr;
+	int smem = 0;
+	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, fn, smem))
+		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
+	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+
+	int ctas_per_sm = 1;
+	const int threads = kConsumerThreads + (use_tma ? 32 : 0);
+	CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
+	if (ctas_per_sm < 1)
+		return fail(ctx, SCOPE_ERR_CUDA, "kernel does not fit on an SM");
+	uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
+	if (grid > P.items)
+		grid = P.items;
+	P.items_per_cta = (P.items + grid - 1) / grid;
+	grid = (P.items + P.items_per_cta - 1) / P.items_per_cta;
+
+	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+	if (ctx->profiling) {
+		if (!ctx->prof_pool.empty()) {
+			ev = ctx->prof_pool.back();
+			ctx->prof_pool.pop_back();
+		} else {
+			CU_TRY(ctx, cudaEventCreate(&ev.first));
+			CU_TRY(ctx, cudaEventCreate(&ev.second));
+		}
+		CU_TRY(ctx, cudaEventRecord(ev.first, stream));
+	}
+	fn<<<grid, threads, smem, stream>>>(P, map_rgb, map_yuv);
+	CU_TRY(ctx, cudaGetLastError());
+	if (ctx->profiling) {
+		CU_TRY(ctx, cudaEventRecord(ev.second, stream));
+		ctx->prof_events.push_back(ev);
+	}
+	ctx->launches++;
+	return SCOPE_OK;
+}
+
+int ensure_vs_acc(scope_ctx *ctx, size_t frames)
+{
+	if (ctx->vs_acc_frames >= frames)
+		return SCOPE_OK;
+	if (ctx->d_vs_acc)
+		cudaFree(ctx->d_vs_acc);
+	ctx->d_vs_acc = nullptr;
+	ctx->vs_acc_frames = 0;
+	cudaError_t e = cudaMalloc(&ctx->d_vs_acc, frames * 65536 * sizeof(uint32_t));
+	if (e != cudaSuccess)
+		return fail(ctx, SCOPE_ERR_NOMEM, "cudaMalloc(vectorscope accumulators)", e);
+	ctx->vs_acc_frames = frames;
+	return SCOPE_OK;
+}
+
+int ensure_hist_scratch(scope_ctx *ctx, size_t frames)
+{
+	if (ctx->hist_scratch_frames >= frames)
+		return SCOPE_OK;
+	if (ctx->d_hist_scratch)
+		cudaFree(ctx->d_hist_scratch);
+	ctx->d_hist_scratch = nullptr;
+	ctx->hist_scratch_frames = 0;
+	cudaError_t e = cudaMalloc(&ctx->d_hist_scratch, frames * 1024 * sizeof(uint32_t));
+	if (e != cudaSuccess)
+		return fail(ctx, SCOPE_ERR_NOMEM, "cudaMalloc(histogram scratch)", e);
+	ctx->hist_scratch_frames = frames;
+	return SCOPE_OK;
+}
+
+// The whole device-side pass for n frames (used by both the device and the host entry points).
+int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, uint32_t n_frames,
+	       size_t frame_stride, const scope_out_device *out, cudaStream_t stream)
+{
+	if (!pr || !s || !out)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	if (s->width == 0 || s->height == 0 || n_frames == 0)
+		return fail(ctx, SCOPE_ERR_INVALID, "empty surface");
+	if (s->linesize < s->width * 4u)
+		return fail(ctx, SCOPE_ERR_INVALID, "linesize < width*4");
+	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
+	const bool want_hist = (pr->scopes & SCOPE_HIST) && (out->hist_counts || out->hist_max);
+	const bool want_wave = (pr->scopes & SCOPE_WAVE) && (out->wave || out->wave_display);
+	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) && (out->vscope || out->vscope_display);
+	if ((pr->scopes & SCOPE_WAVE) && out->wave_display && !out->wave)
+		return fail(ctx, SCOPE_ERR_INVALID, "wave_display needs wave");
+
+	int hsrc = SRC_NONE, wsrc = SRC_NONE;
+	uint32_t hmask = 0, wmask = 0;
+	if (want_hist)
+		decode_components(pr->hist_components, hsrc, hmask);
+	if (want_wave)
+		decode_components(pr->wave_components, wsrc, wmask);
+
+	uint32_t *hist = out->hist_counts;
+	size_t hist_stride = 1024;
+	if (want_hist && !hist) {
+		int r = ensure_hist_scratch(ctx, n_frames);
+		if (r)
+			return r;
+		hist = ctx->d_hist_scratch;
+	}
+	if (want_hist)
+		CU_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)n_frames * 1024 * sizeof(uint32_t), stream));
+	if (want_wave && wsrc == SRC_NONE) // components select no plane: the reference leaves zeros
+		CU_TRY(ctx, cudaMemsetAsync(out->wave, 0, (size_t)n_frames * scope_wave_bytes(s->width), stream));
+	if (want_vs) {
+		int r = ensure_vs_acc(ctx, n_frames);
+		if (r)
+			return r;
+		CU_TRY(ctx, cudaMemsetAsync(ctx->d_vs_acc, 0, (size_t)n_frames * 65536 * sizeof(uint32_t), stream));
+	}
+
+	Request rq{};
+	rq.rgb = s->rgb_data;
+	rq.yuv = surface ? s->yuv_data : nullptr;
+	rq.linesize = s->linesize;
+	rq.width = s->width;
+	rq.height = s->height;
+	rq.n_frames = n_frames;
+	rq.frame_stride = frame_stride;
+	rq.colorspace = s->colorspace;
+	rq.surface = surface;
+	rq.hist = hist;
+	rq.hist_stride = hist_stride;
+	rq.wave = out->wave;
+	rq.wave_stride = scope_wave_bytes(s->width);
+	rq.wave_pairs = nullptr;
+	rq.x_offset = 0;
+	rq.out_width = s->width;
+	rq.partial = false;
+	rq.vs_acc = ctx->d_vs_acc;
+	rq.vs_stride = 65536;
+
+	// One launch when histogram and waveform read the same plane (or only one of them is
+	// on); otherwise the histogram gets its own launch with the vectorscope riding on the
+	// waveform's.  Mirrors the ROI fan-out (roi.c:329-341): same surface, every scope.
+	if (hsrc != SRC_NONE && wsrc != SRC_NONE && hsrc != wsrc) {
+		Request a = rq;
+		a.src = wsrc;
+		a.bins_mask = wmask;
+		a.wave_mask = wmask;
+		a.hist_mask = 0;
+		a.vscope = want_vs;
+		int r = launch_strip(ctx, a, stream);
+		if (r)
+			return r;
+		Request b = rq;
+		b.src = hsrc;
+		b.bins_mask = hmask;
+		b.hist_mask = hmask;
+		b.wave_mask = 0;
+		b.vscope = false;
+		r = launch_strip(ctx, b, stream);
+		if (r)
+			return r;
+	} else {
+		Request a = rq;
+		a.src = hsrc != SRC_NONE ? hsrc : wsrc;
+		a.hist_mask = hmask;
+		a.wave_mask = wmask;
+		a.bins_mask = hmask | wmask;
+		a.vscope = want_vs;
+		int r = launch_strip(ctx, a, stream);
+		if (r)
+			return r;
+	}
+
+	if (want_vs) {
+		const float k = pr->vscope_intensity > 0 ? (float)pr->vscope_intensity : 1.0f;
+		dim3 grid(65536 / 1024, n_frames);
+		vscope_finalize_kernel<<<grid, 256, 0, stream>>>(ctx->d_vs_acc, 65536, out->vscope,
+								  pr->vscope_intensity > 0 ? out->vscope_display : nullptr,
+								  65536, k);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	if (want_hist && out->hist_max) {
+		hist_max_kernel<<<n_frames, 256, 0, stream>>>(hist, hist_stride, out->hist_max, pr->hist_components,
+							       s->width, s->height, pr->level_fixed_value,
+							       pr->level_ratio_value);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	if (want_wave && out->wave_display && pr->wave_intensity > 0) {
+		const size_t words = (size_t)n_frames * scope_wave_bytes(s->width) / 4;
+		wave_display_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(out->wave, out->wave_display, words,
+										       (float)pr->wave_intensity);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	return SCOPE_OK;
+}
+
+// histogram post-pass on the host: exactly histogram.c:404-417 (same libm logf as the reference)
+void hist_to_float(const scope_params *pr, const uint32_t *counts, uint32_t *hi_max, float *out)
+{
+	if (pr->logscale) {
+		memcpy(out, counts, sizeof(uint32_t) * 1024);
+		for (int j = 0, mask = 0x44; j < 3; j++, mask >>= 1) {
+			if (!(pr->hist_components & (uint32_t)mask))
+				continue;
+			const float sc = 1.0f / logf((float)(hi_max[j] + 1));
+			for (int i = 0; i < 256; i++)
+				out[i * 4 + j] = counts[i * 4 + j] ? logf((float)(counts[i * 4 + j] + 1)) * sc : 0;
+			hi_max[j] = 1;
+		}
+	} else {
+		for (int i = 0; i < 1024; i++)
+			out[i] = (float)counts[i];
+	}
+}
+
+int ensure_slot(scope_ctx *ctx, RingSlot &sl, size_t in_bytes, uint32_t width)
+{
+	if (!sl.stream) {
+		CU_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+		CU_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+		CU_TRY(ctx, cudaMalloc(&sl.d_hist, 1024 * 4));
+		CU_TRY(ctx, cudaMalloc(&sl.d_hist_max, 16));
+		CU_TRY(ctx, cudaMalloc(&sl.d_vscope, 65536));
+		CU_TRY(ctx, cudaMalloc(&sl.d_vscope_disp, 65536));
+	}
+	if (sl.d_in_bytes < in_bytes) {
+		if (sl.d_in)
+			cudaFree(sl.d_in);
+		sl.d_in = nullptr;
+		sl.d_in_bytes = 0;
+		cudaError_t e = cudaMalloc(&sl.d_in, in_bytes);
+		if (e != cudaSuccess)
+			return fail(ctx, SCOPE_ERR_NOMEM, "cudaMalloc(input staging)", e);
+		sl.d_in_bytes = in_bytes;
+	}
+	const size_t wb = scope_wave_bytes(width);
+	if (sl.d_wave_bytes < wb) {
+		if (sl.d_wave)
+			cudaFree(sl.d_wave);
+		if (sl.d_wave_disp)
+			cudaFree(sl.d_wave_disp);
+		sl.d_wave = sl.d_wave_disp = nullptr;
+		sl.d_wave_bytes = 0;
+		cudaError_t e = cudaMalloc(&sl.d_wave, wb);
+		if (e == cudaSuccess)
+			e = cudaMalloc(&sl.d_wave_disp, wb);
+		if (e != cudaSuccess)
+			return fail(ctx, SCOPE_ERR_NOMEM, "cudaMalloc(waveform staging)", e);
+		sl.d_wave_bytes = wb;
+	}
+	const size_t rb = 4096 + 16 + 65536 * 2 + wb * 2;
+	if (sl.h_res_bytes < rb) {
+		if (sl.h_res)
+			cudaFreeHost(sl.h_res);
+		sl.h_res = nullptr;
+		sl.h_res_bytes = 0;
+		cudaError_t e = cudaHostAlloc(&sl.h_res, rb, cudaHostAllocDefault);
+		if (e != cudaSuccess)
+			return fail(ctx, SCOPE_ERR_NOMEM, "cudaHostAlloc(result staging)", e);
+		sl.h_res_bytes = rb;
+	}
+	return SCOPE_OK;
+}
+
+int submit_host(scope_ctx *ctx, int slot, const scope_params *pr, const scope_surface *s)
+{
+	if (!pr || !s)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	if (slot < 0 || slot >= SCOPE_RING_SLOTS)
+		return fail(ctx, SCOPE_ERR_INVALID, "bad ring slot");
+	RingSlot &sl = ctx->ring[slot];
+	if (sl.in_flight)
+		return fail(ctx, SCOPE_ERR_BUSY, "ring slot still in flight");
+	if (s->width == 0 || s->height == 0)
+		return fail(ctx, SCOPE_ERR_INVALID, "empty surface");
+	if (s->linesize < s->width * 4u)
+		return fail(ctx, SCOPE_ERR_INVALID, "linesize < width*4");
+	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
+	// same early-outs as the reference callbacks (histogram.c:436-441, waveform.c:276-281,
+	// vectorscope.c:252-253): a missing plane means "do nothing, keep the previous result"
+	int hsrc, wsrc;
+	uint32_t m;
+	decode_components(pr->hist_components, hsrc, m);
+	decode_components(pr->wave_components, wsrc, m);
+	const bool hist_on = pr->scopes & SCOPE_HIST, wave_on = pr->scopes & SCOPE_WAVE, vs_on = pr->scopes & SCOPE_VSCOPE;
+	const bool need_rgb = !surface || (hist_on && hsrc == SRC_RGB) || (wave_on && wsrc == SRC_RGB);
+	const bool need_yuv = surface && ((hist_on && hsrc == SRC_YUV) || (wave_on && wsrc == SRC_YUV) || vs_on);
+	if ((need_rgb && !s->rgb_data) || (need_yuv && !s->yuv_data))
+		return fail(ctx, SCOPE_ERR_INVALID, "a plane the request needs is NULL");
+
+	// device copy: rows packed at a 16-byte-multiple pitch so the TMA path applies
+	const uint32_t pitch = (s->width * 4u + 15u) & ~15u;
+	const size_t plane_bytes = (size_t)pitch * s->height;
+	int r = ensure_slot(ctx, sl, plane_bytes * 2, s->width);
+	if (r)
+		return r;
+	uint8_t *d_rgb = sl.d_in, *d_yuv = sl.d_in + plane_bytes;
+	if (need_rgb)
+		CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb, pitch, s->rgb_data, s->linesize, (size_t)s->width * 4, s->height,
+					      cudaMemcpyHostToDevice, sl.stream));
+	if (need_yuv)
+		CU_TRY(ctx, cudaMemcpy2DAsync(d_yuv, pitch, s->yuv_data, s->linesize, (size_t)s->width * 4, s->height,
+					      cudaMemcpyHostToDevice, sl.stream));
+
+	scope_surface ds = *s;
+	ds.rgb_data = need_rgb ? d_rgb : nullptr;
+	ds.yuv_data = need_yuv ? d_yuv : nullptr;
+	ds.linesize = pitch;
+	scope_out_device od{};
+	od.hist_counts = sl.d_hist;
+	od.hist_max = sl.d_hist_max;
+	od.wave = sl.d_wave;
+	od.wave_display = pr->wave_intensity > 0 ? sl.d_wave_disp : nullptr;
+	od.vscope = sl.d_vscope;
+	od.vscope_display = pr->vscope_intensity > 0 ? sl.d_vscope_disp : nullptr;
+	r = run_device(ctx, pr, &ds, 1, plane_bytes, &od, sl.stream);
+	if (r)
+		return r;
+
+	// results -> pinned staging
+	const size_t wb = scope_wave_bytes(s->width);
+	uint8_t *h = sl.h_res;
+	if (hist_on) {
+		CU_TRY(ctx, cudaMemcpyAsync(h, sl.d_hist, 4096, cudaMemcpyDeviceToHost, sl.stream));
+		CU_TRY(ctx, cudaMemcpyAsync(h + 4096, sl.d_hist_max, 16, cudaMemcpyDeviceToHost, sl.stream));
+	}
+	if (vs_on) {
+		CU_TRY(ctx, cudaMemcpyAsync(h + 4112, sl.d_vscope, 65536, cudaMemcpyDeviceToHost, sl.stream));
+		if (pr->vscope_intensity > 0)
+			CU_TRY(ctx, cudaMemcpyAsync(h + 4112 + 65536, sl.d_vscope_disp, 65536, cudaMemcpyDeviceToHost,
+						    sl.stream));
+	}
+	if (wave_on) {
+		CU_TRY(ctx, cudaMemcpyAsync(h + 4112 + 131072, sl.d_wave, wb, cudaMemcpyDeviceToHost, sl.stream));
+		if (pr->wave_intensity > 0)
+			CU_TRY(ctx, cudaMemcpyAsync(h + 4112 + 131072 + wb, sl.d_wave_disp, wb, cudaMemcpyDeviceToHost,
+						    sl.stream));
+	}
+	CU_TRY(ctx, cudaEventRecord(sl.done, sl.stream));
+	sl.params = *pr;
+	sl.width = s->width;
+	sl.height = s->height;
+	sl.in_flight = true;
+	return SCOPE_OK;
+}
+
+int wait_host(scope_ctx *ctx, int slot, const scope_out_host *out)
+{
+	if (slot < 0 || slot >= SCOPE_RING_SLOTS)
+		return fail(ctx, SCOPE_ERR_INVALID, "bad ring slot");
+	RingSlot &sl = ctx->ring[slot];
+	if (!sl.in_flight)
+		return fail(ctx, SCOPE_ERR_INVALID, "ring slot has no submission");
+	cudaError_t e = cudaEventSynchronize(sl.done);
+	sl.in_flight = false;
+	if (e != cudaSuccess)
+		return fail(ctx, SCOPE_ERR_CUDA, "cudaEventSynchronize", e);
+	if (!out)
+		return SCOPE_OK;
+	const scope_params &pr = sl.params;
+	const size_t wb = scope_wave_bytes(sl.width);
+	const uint8_t *h = sl.h_res;
+	if (pr.scopes & SCOPE_HIST) {
+		const uint32_t *counts = reinterpret_cast<const uint32_t *>(h);
+		uint32_t hi[3];
+		memcpy(hi, h + 4096, sizeof hi);
+		if (out->hist_counts)
+			memcpy(out->hist_counts, counts, 4096);
+		if (out->hist_float) {
+			hist_to_float(&pr, counts, hi, out->hist_float);
+		} else if (pr.logscale) {
+			for (int j = 0, mask = 0x44; j < 3; j++, mask >>= 1)
+				if (pr.hist_components & (uint32_t)mask)
+					hi[j] = 1;
+		}
+		if (out->hist_max)
+			memcpy(out->hist_max, hi, sizeof hi);
+	}
+	if (pr.scopes & SCOPE_VSCOPE) {
+		if (out->vscope)
+			memcpy(out->vscope, h + 4112, 65536);
+		if (out->vscope_display && pr.vscope_intensity > 0)
+			memcpy(out->vscope_display, h + 4112 + 65536, 65536);
+	}
+	if (pr.scopes & SCOPE_WAVE) {
+		if (out->wave)
+			memcpy(out->wave, h + 4112 + 131072, wb);
+		if (out->wave_display && pr.wave_intensity > 0)
+			memcpy(out->wave_display, h + 4112 + 131072 + wb, wb);
+	}
+	return SCOPE_OK;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev)
+	{
+		cudaGetDevice(&prev);
+		if (prev != dev)
+			cudaSetDevice(dev);
+		else
+			prev = -1;
+	}
+	~DeviceGuard()
+	{
+		if (prev >= 0)
+			cudaSetDevice(prev);
+	}
+};
+
+} // namespace
+
+// ===========================================================================
+// C-ABI
+// ===========================================================================
+extern "C" {
+
+int scope_abi_version(void)
+{
+	return SCOPE_ABI_VERSION;
+}
+
+size_t scope_wave_bytes(uint32_t width)
+{
+	return (size_t)256 * width * 4;
+}
+
+size_t scope_partial_wave_words(uint32_t width)
+{
+	return (size_t)256 * width * 2;
+}
+
+int scope_ctx_create(int device, scope_ctx **out_ctx)
+{
+	if (!out_ctx)
+		return fail(nullptr, SCOPE_ERR_INVALID, "out_ctx is NULL");
+	*out_ctx = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(nullptr, SCOPE_ERR_NO_DEVICE,
+			    "no CUDA device available (libscope_b200 has no CPU fallback)", e);
+	if (device < 0) {
+		e = cudaGetDevice(&device);
+		if (e != cudaSuccess)
+			return fail(nullptr, SCOPE_ERR_CUDA, "cudaGetDevice", e);
+	}
+	if (device >= count)
+		return fail(nullptr, SCOPE_ERR_INVALID, "device index out of range");
+	DeviceGuard guard(device);
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess)
+		return fail(nullptr, SCOPE_ERR_CUDA, "cudaGetDeviceProperties", e);
+	if (prop.major != 10)
+		return fail(nullptr, SCOPE_ERR_NO_DEVICE,
+			    "device is not compute capability 10.x: this library carries sm_100a code only");
+	scope_ctx *ctx = new (std::nothrow) scope_ctx();
+	if (!ctx)
+		return fail(nullptr, SCOPE_ERR_NOMEM, "out of host memory");
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	void *fn = nullptr;
+	cudaDriverEntryPointQueryResult qres;
+	e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+	if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+		ctx->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+	else
+		(void)cudaGetLastError();
+	*out_ctx = ctx;
+	return SCOPE_OK;
+}
+
+void scope_ctx_destroy(scope_ctx *ctx)
+{
+	if (!ctx)
+		return;
+	DeviceGuard guard(ctx->device);
+	for (RingSlot &sl : ctx->ring) {
+		if (sl.stream)
+			cudaStreamSynchronize(sl.stream);
+		cudaFree(sl.d_in);
+		cudaFree(sl.d_hist);
+		cudaFree(sl.d_hist_max);
+		cudaFree(sl.d_wave);
+		cudaFree(sl.d_wave_disp);
+		cudaFree(sl.d_vscope);
+		cudaFree(sl.d_vscope_disp);
+		if (sl.h_res)
+			cudaFreeHost(sl.h_res);
+		if (sl.done)
+			cudaEventDestroy(sl.done);
+		if (sl.stream)
+			cudaStreamDestroy(sl.stream);
+	}
+	cudaFree(ctx->d_vs_acc);
+	cudaFree(ctx->d_hist_scratch);
+	for (auto &ev : ctx->prof_events)
+		ctx->prof_pool.push_back(ev);
+	for (auto &ev : ctx->prof_pool) {
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	delete ctx;
+}
+
+const char *scope_last_error(const scope_ctx *ctx)
+{
+	return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+uint64_t scope_launch_count(const scope_ctx *ctx)
+{
+	return ctx ? ctx->launches : 0;
+}
+
+int scope_sm_count(const scope_ctx *ctx)
+{
+	return ctx ? ctx->sm_count : 0;
+}
+
+int scope_accumulate_device(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
+			    uint32_t n_frames, size_t frame_stride, const struct scope_out_device *out, void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	return run_device(ctx, params, surface, n_frames, frame_stride, out, (cudaStream_t)stream);
+}
+
+int scope_submit_host(scope_ctx *ctx, int slot, const struct scope_params *params, const struct scope_surface *surface)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	return submit_host(ctx, slot, params, surface);
+}
+
+int scope_wait_host(scope_ctx *ctx, int slot, const struct scope_out_host *out)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	return wait_host(ctx, slot, out);
+}
+
+int scope_accumulate_host(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
+			  const struct scope_out_host *out)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	// use the first idle slot so a pending stream submission is not disturbed
+	int slot = -1;
+	for (int i = 0; i < SCOPE_RING_SLOTS; i++)
+		if (!ctx->ring[i].in_flight) {
+			slot = i;
+			break;
+		}
+	if (slot < 0)
+		return fail(ctx, SCOPE_ERR_BUSY, "all ring slots in flight");
+	int r = submit_host(ctx, slot, params, surface);
+	if (r)
+		return r;
+	return wait_host(ctx, slot, out);
+}
+
+int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *pr, const struct scope_surface *tile,
+			     uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
+			     void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!pr || !tile || !partial)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	if (tile->width == 0 || tile->height == 0 || x_offset + tile->width > full_width)
+		return fail(ctx, SCOPE_ERR_INVALID, "bad tile geometry");
+	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
+	const bool want_hist = (pr->scopes & SCOPE_HIST) && partial->hist_counts;
+	const bool want_wave = (pr->scopes & SCOPE_WAVE) && partial->wave_pairs;
+	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) && partial->vscope_counts;
+	int hsrc = SRC_NONE, wsrc = SRC_NONE;
+	uint32_t hmask = 0, wmask = 0;
+	if (want_hist)
+		decode_components(pr->hist_components, hsrc, hmask);
+	if (want_wave)
+		decode_components(pr->wave_components, wsrc, wmask);
+	Request rq{};
+	rq.rgb = tile->rgb_data;
+	rq.yuv = surface ? tile->yuv_data : nullptr;
+	rq.linesize = tile->linesize;
+	rq.width = tile->width;
+	rq.height = tile->height;
+	rq.n_frames = 1;
+	rq.frame_stride = 0;
+	rq.colorspace = tile->colorspace;
+	rq.surface = surface;
+	rq.hist = partial->hist_counts;
+	rq.hist_stride = 1024;
+	rq.wave = nullptr;
+	rq.wave_stride = 0;
+	rq.wave_pairs = partial->wave_pairs;
+	rq.x_offset = x_offset;
+	rq.out_width = full_width;
+	rq.partial = true;
+	rq.vs_acc = partial->vscope_counts;
+	rq.vs_stride = 65536;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (hsrc != SRC_NONE && wsrc != SRC_NONE && hsrc != wsrc) {
+		Request a = rq;
+		a.src = wsrc;
+		a.bins_mask = a.wave_mask = wmask;
+		a.hist_mask = 0;
+		a.vscope = want_vs;
+		int r = launch_strip(ctx, a, st);
+		if (r)
+			return r;
+		Request b = rq;
+		b.src = hsrc;
+		b.bins_mask = b.hist_mask = hmask;
+		b.wave_mask = 0;
+		b.vscope = false;
+		return launch_strip(ctx, b, st);
+	}
+	Request a = rq;
+	a.src = hsrc != SRC_NONE ? hsrc : wsrc;
+	a.hist_mask = hmask;
+	a.wave_mask = wmask;
+	a.bins_mask = hmask | wmask;
+	a.vscope = want_vs;
+	return launch_strip(ctx, a, st);
+}
+
+int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
+			   const struct scope_partial_device *partial, const struct scope_out_device *out, void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!pr || !partial || !out)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	cudaStream_t st = (cudaStream_t)stream;
+	if ((pr->scopes & SCOPE_VSCOPE) && partial->vscope_counts && (out->vscope || out->vscope_display)) {
+		const float k = pr->vscope_intensity > 0 ? (float)pr->vscope_intensity : 1.0f;
+		vscope_finalize_kernel<<<dim3(64, 1), 256, 0, st>>>(partial->vscope_counts, 65536, out->vscope,
+								     pr->vscope_intensity > 0 ? out->vscope_display : nullptr,
+								     65536, k);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	if ((pr->scopes & SCOPE_WAVE) && partial->wave_pairs && out->wave) {
+		const size_t n_px = (size_t)256 * full_width;
+		wave_pairs_finalize_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(partial->wave_pairs, out->wave,
+											      n_px);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+		if (out->wave_display && pr->wave_intensity > 0) {
+			wave_display_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(out->wave, out->wave_display, n_px,
+										       (float)pr->wave_intensity);
+			CU_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
+	}
+	if ((pr->scopes & SCOPE_HIST) && partial->hist_counts) {
+		if (out->hist_counts && out->hist_counts != partial->hist_counts)
+			CU_TRY(ctx, cudaMemcpyAsync(out->hist_counts, partial->hist_counts, 4096, cudaMemcpyDeviceToDevice,
+						    st));
+		if (out->hist_max) {
+			hist_max_kernel<<<1, 256, 0, st>>>(partial->hist_counts, 1024, out->hist_max, pr->hist_components,
+							    full_width, full_height, pr->level_fixed_value,
+							    pr->level_ratio_value);
+			CU_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
+	}
+	return SCOPE_OK;
+}
+
+int scope_profile_enable(scope_ctx *ctx, int on)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	ctx->profiling = on != 0;
+	return SCOPE_OK;
+}
+
+int scope_profile_read(scope_ctx *ctx, float *ms_out, int max_entries)
+{
+	if (!ctx)
+		return -1;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	int n = 0;
+	for (auto &ev : ctx->prof_events) {
+		float ms = 0.0f;
+		if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess &&
+		    ms_out && n < max_entries)
+			ms_out[n++] = ms;
+		ctx->prof_pool.push_back(ev);
+	}
+	ctx->prof_events.clear();
+	return n;
+}
+
+void *scope_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void scope_host_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+// test hook (not part of the drop-in surface): the kernel's transform over all 2^24 colours
+int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out /* device, 1<<24 u32 */, void *stream)
+{
+	if (!ctx || !d_out)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	yuv_table_kernel<<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(coef_for(colorspace), d_out);
+	CU_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return SCOPE_OK;
+}
+
+} // extern "C"

@@ -77,7 +77,7 @@ class Oracle:
         self.lib = L = C.CDLL(path)
         L.orc_rgb_to_yuv.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
         L.orc_rgb_to_yuv.restype = None
-        L.orc_rgb_to_yuv_table.argtypes = [C.c_int, C.c_void_p]
+        L.orc_rgb_to_yuv_table.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.orc_rgb_to_yuv_table.restype = C.c_int
         L.orc_calc_colorspace.argtypes = [C.c_int]
         L.orc_calc_colorspace.restype = C.c_int
@@ -100,9 +100,10 @@ class Oracle:
         self.lib.orc_rgb_to_yuv(_ptr(bgra), ls, w, h, colorspace, out.ctypes.data, w * 4)
         return out
 
-    def rgb_to_yuv_table(self, colorspace: int) -> Tuple[np.ndarray, bool]:
+    def rgb_to_yuv_table(self, colorspace: int, strict: bool = False) -> Tuple[np.ndarray, bool]:
+        """All 2^24 colours: out[r<<16|g<<8|b] = u | y<<8 | v<<16; second value = clamp ever active."""
         out = np.zeros(1 << 24, np.uint32)
-        clamp = self.lib.orc_rgb_to_yuv_table(colorspace, out.ctypes.data)
+        clamp = self.lib.orc_rgb_to_yuv_table(colorspace, int(strict), out.ctypes.data)
         return out, bool(clamp)
 
     def calc_colorspace(self, cs: int) -> int:

@@ -45,14 +45,22 @@ struct orc_surface {
 };
 
 /* ------------------------------------------------------------------ */
-/* RGB -> YUV, pinned definition:                     */
-/*   xf = (float)X / 255.0f                                            */
-/*   t  = ((c0*rf + c1*gf) + c2*bf) + off      fp32, in this order,     */
-/*        no contraction (build with -ffp-contract=off)                 */
-/*   q  = (uint8_t)floorf(min(max(t,0),1) * 255.0f + 0.5f)              */
-/* coefficients exactly as printed in data/common.effect:27-29,38-40;   */
-/* off = 0.5f - 1.0f/256.0f (U), 0 (Y), 0.5f (V).                       */
-/* Output bytes [U, Y, V, 255] (B<-z, G<-y, R<-x, A<-1).               */
+/* RGB -> YUV, pinned definition ("contracted", the one the product    */
+/* implements; DESIGN.md §3 explains the choice):                       */
+/*   xf = (float)X / 255.0f                     (correctly rounded)     */
+/*   p  = c0*rf ; p = fma(c1,gf,p) ; p = fma(c2,bf,p) ; t = p + off     */
+/*        i.e. the mul/mad/mad/add sequence a shader compiler emits for */
+/*        `c0*r + c1*g + c2*b + off` (data/common.effect:27-29,38-40)   */
+/*   q  = (uint8_t)floorf(fmaf(min(max(t,0),1), 255.0f, 0.5f))          */
+/* coefficients exactly as printed in the effect file; off = 0.5f -     */
+/* 1.0f/256.0f (U), 0 (Y), 0.5f (V).  Output bytes [U, Y, V, 255]       */
+/* (B<-z, G<-y, R<-x, A<-1).                                            */
+/*                                                                      */
+/* "strict" variant = SURVEY.md §8(c)'s first draft (every product and  */
+/* sum rounded separately, no FMA anywhere); kept so the tests can      */
+/* report how many of the 2^24 colours the two definitions disagree on. */
+/* Build with -ffp-contract=off so the compiler adds no contraction of  */
+/* its own.                                                             */
 /* ------------------------------------------------------------------ */
 struct yuv_coeffs {
 	float u[3], y[3], v[3];
@@ -69,15 +77,32 @@ static const struct yuv_coeffs k_bt709 = {
 	{+0.439216f, -0.398941f, -0.040273f},
 };
 
-static inline uint8_t quantise_unorm8(float t)
+static inline float clamp01(float t)
 {
-	t = fminf(fmaxf(t, 0.0f), 1.0f);
-	float s = t * 255.0f;
+	return fminf(fmaxf(t, 0.0f), 1.0f);
+}
+
+static inline uint8_t quantise_contracted(float t)
+{
+	return (uint8_t)floorf(fmaf(clamp01(t), 255.0f, 0.5f));
+}
+
+static inline uint8_t quantise_strict(float t)
+{
+	float s = clamp01(t) * 255.0f;
 	s = s + 0.5f;
 	return (uint8_t)floorf(s);
 }
 
-static inline float dot3_off(const float c[3], float r, float g, float b, float off)
+static inline float dot3_contracted(const float c[3], float r, float g, float b, float off)
+{
+	float p = c[0] * r;
+	p = fmaf(c[1], g, p);
+	p = fmaf(c[2], b, p);
+	return p + off;
+}
+
+static inline float dot3_strict(const float c[3], float r, float g, float b, float off)
 {
 	float a0 = c[0] * r;
 	float a1 = c[1] * g;
@@ -88,16 +113,19 @@ static inline float dot3_off(const float c[3], float r, float g, float b, float 
 	return s;
 }
 
+#define OFF_U (0.5f - 1.0f / 256.0f)
+#define OFF_Y 0.0f
+#define OFF_V 0.5f
+
 ORC_API void orc_rgb_to_yuv_pixel(int colorspace, uint8_t r8, uint8_t g8, uint8_t b8, uint8_t out_uyv[3])
 {
 	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
 	const float r = (float)r8 / 255.0f;
 	const float g = (float)g8 / 255.0f;
 	const float b = (float)b8 / 255.0f;
-	const float off_u = 0.5f - 1.0f / 256.0f;
-	out_uyv[0] = quantise_unorm8(dot3_off(k->u, r, g, b, off_u));
-	out_uyv[1] = quantise_unorm8(dot3_off(k->y, r, g, b, 0.0f));
-	out_uyv[2] = quantise_unorm8(dot3_off(k->v, r, g, b, 0.5f));
+	out_uyv[0] = quantise_contracted(dot3_contracted(k->u, r, g, b, OFF_U));
+	out_uyv[1] = quantise_contracted(dot3_contracted(k->y, r, g, b, OFF_Y));
+	out_uyv[2] = quantise_contracted(dot3_contracted(k->v, r, g, b, OFF_V));
 }
 
 /* Whole plane: BGRA in, [U,Y,V,255] out.  Alpha of the source is ignored
@@ -120,25 +148,34 @@ ORC_API void orc_rgb_to_yuv(const uint8_t *bgra, uint32_t linesize, uint32_t wid
 }
 
 /* Exhaustive helper for tests: all 2^24 (r,g,b) -> packed u | y<<8 | v<<16,
- * index = r<<16 | g<<8 | b.  Also reports whether the [0,1] clamp ever
- * changed a value (it must not: the GPU kernel relies on that). */
-ORC_API int orc_rgb_to_yuv_table(int colorspace, uint32_t *out /* 1<<24 entries */)
+ * index = r<<16 | g<<8 | b.  strict != 0 selects the no-FMA variant.  Returns
+ * 1 if the [0,1] clamp ever changed a value (it must not: the GPU kernel
+ * relies on that and omits it). */
+ORC_API int orc_rgb_to_yuv_table(int colorspace, int strict, uint32_t *out /* 1<<24 entries */)
 {
 	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
-	const float off_u = 0.5f - 1.0f / 256.0f;
 	int clamp_active = 0;
 	for (uint32_t r8 = 0; r8 < 256; r8++)
 		for (uint32_t g8 = 0; g8 < 256; g8++)
 			for (uint32_t b8 = 0; b8 < 256; b8++) {
 				const float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, b = (float)b8 / 255.0f;
-				const float tu = dot3_off(k->u, r, g, b, off_u);
-				const float ty = dot3_off(k->y, r, g, b, 0.0f);
-				const float tv = dot3_off(k->v, r, g, b, 0.5f);
+				float tu, ty, tv;
+				uint32_t qu, qy, qv;
+				if (strict) {
+					tu = dot3_strict(k->u, r, g, b, OFF_U);
+					ty = dot3_strict(k->y, r, g, b, OFF_Y);
+					tv = dot3_strict(k->v, r, g, b, OFF_V);
+					qu = quantise_strict(tu), qy = quantise_strict(ty), qv = quantise_strict(tv);
+				} else {
+					tu = dot3_contracted(k->u, r, g, b, OFF_U);
+					ty = dot3_contracted(k->y, r, g, b, OFF_Y);
+					tv = dot3_contracted(k->v, r, g, b, OFF_V);
+					qu = quantise_contracted(tu), qy = quantise_contracted(ty),
+					qv = quantise_contracted(tv);
+				}
 				if (tu < 0.0f || tu > 1.0f || ty < 0.0f || ty > 1.0f || tv < 0.0f || tv > 1.0f)
 					clamp_active = 1;
-				out[(r8 << 16) | (g8 << 8) | b8] = (uint32_t)quantise_unorm8(tu) |
-								    ((uint32_t)quantise_unorm8(ty) << 8) |
-								    ((uint32_t)quantise_unorm8(tv) << 16);
+				out[(r8 << 16) | (g8 << 8) | b8] = qu | (qy << 8) | (qv << 16);
 			}
 	return clamp_active;
 }
@@ -319,8 +356,6 @@ ORC_API void orc_apply_intensity(const uint8_t *bins, size_t n, int intensity, u
 		r = r * k;
 		if (r > 1.0f)
 			r = 1.0f;
-		float q = r * 255.0f;
-		q = q + 0.5f;
-		out[i] = (uint8_t)floorf(q);
+		out[i] = (uint8_t)floorf(fmaf(r, 255.0f, 0.5f));
 	}
 }

@@ -1,0 +1,134 @@
+"""CPU tests of the checker itself (no GPU):
+  * oracle restatement == the reference's own loops (oracle/_ref, when built here)
+  * oracle restatement == the committed golden vectors (generated FROM the reference by
+    tests/golden/make_golden.py) — this one also runs on the GPU box, where /root/reference
+    and possibly oracle/_ref do not exist
+  * hand-checkable known answers
+  * the pinned transform's arithmetic facts the CUDA kernel relies on
+"""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scope_golden.npz")
+COMPONENTS = [0x07, 0x20, 0x50, 0x70, 0x05, 0x42]
+CASES = ["ramp", "random", "solid", "alpha", "natural", "pitched"]
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_golden(oracle, golden, case):
+    rgb, yuv, width = golden[f"{case}/rgb"], golden[f"{case}/yuv"], int(golden[f"{case}/width"])
+    height = rgb.shape[0]
+    for comp in COMPONENTS:
+        counts = oracle.histogram_counts(comp, rgb, yuv, width=width)
+        for log in (0, 1):
+            flt, hi = oracle.histogram_post(comp, width, height, counts, logscale=bool(log))
+            assert np.array_equal(flt.view(np.uint32), golden[f"{case}/hist/{comp:02x}/log{log}"].view(np.uint32))
+            assert np.array_equal(hi, golden[f"{case}/hist_max/{comp:02x}/log{log}"])
+        assert np.array_equal(oracle.histogram_post(comp, width, height, counts, level_fixed=100)[1],
+                              golden[f"{case}/hist_max/{comp:02x}/fixed100"])
+        assert np.array_equal(oracle.histogram_post(comp, width, height, counts, level_ratio=5)[1],
+                              golden[f"{case}/hist_max/{comp:02x}/ratio5"])
+        assert np.array_equal(oracle.waveform(comp, rgb, yuv, width=width), golden[f"{case}/wave/{comp:02x}"])
+    assert np.array_equal(oracle.vectorscope(yuv, width=width), golden[f"{case}/vscope"])
+
+
+def test_oracle_matches_reference_loops(oracle, ref, pkg):
+    """bigger, seeded, straight against the reference's compiled loops (build container only)"""
+    fr = pkg.frames
+    frames = [fr.ramp(1920, 1080), fr.random(641, 363, 3), fr.solid(320, 300), fr.alpha_stripes(333, 257),
+              fr.natural(400, 300, 5)]
+    for f in frames:
+        yuv = oracle.rgb_to_yuv(f, 2)
+        for comp in (0x07, 0x20, 0x50, 0x70, 0x13, 0x64):
+            c = oracle.histogram_counts(comp, f, yuv)
+            for kw in (dict(), dict(logscale=True), dict(level_fixed=77), dict(level_ratio=9)):
+                post, hi = oracle.histogram_post(comp, f.shape[1], f.shape[0], c, **kw)
+                rp, rhi = ref.histogram(comp, f, yuv, **kw)
+                assert np.array_equal(post.view(np.uint32), rp.view(np.uint32))
+                assert np.array_equal(hi, rhi)
+            assert np.array_equal(oracle.waveform(comp, f, yuv), ref.waveform(comp, f, yuv))
+        assert np.array_equal(oracle.vectorscope(yuv), ref.vectorscope(yuv))
+
+
+def test_config1_ramp_histogram_closed_form(oracle, pkg):
+    """BASELINE config 1: 1920x1080 ramp, histogram RGB, bit-exact against the closed form."""
+    w, h = 1920, 1080
+    f = pkg.frames.ramp(w, h)
+    c = oracle.histogram_counts(0x07, f, None).reshape(256, 4)
+    xs, ys = np.arange(w) & 255, np.arange(h) & 255
+    exp_b = np.bincount(xs, minlength=256) * h
+    exp_g = np.bincount(ys, minlength=256) * w
+    exp_r = np.bincount(((np.arange(w)[None, :] + np.arange(h)[:, None]) & 255).ravel(), minlength=256)
+    assert np.array_equal(c[:, 2], exp_b) and np.array_equal(c[:, 1], exp_g) and np.array_equal(c[:, 0], exp_r)
+    assert (c[:, 3] == 0).all() and c.sum() == 3 * w * h
+
+
+def test_known_answers_solid(oracle, pkg):
+    w, h = 64, 300
+    f = pkg.frames.solid(w, h, (7, 100, 200, 255))
+    yuv = oracle.rgb_to_yuv(f, 2)
+    c = oracle.histogram_counts(0x07, f, yuv)
+    assert c[200 * 4 + 0] == w * h and c[100 * 4 + 1] == w * h and c[7 * 4 + 2] == w * h and c.sum() == 3 * w * h
+    wv = oracle.waveform(0x07, f, yuv)
+    assert (wv[255 - 7, :, 0] == 255).all() and (wv[255 - 100, :, 1] == 255).all() and (wv[:, :, 3] == 0).all()
+    vs = oracle.vectorscope(yuv)
+    u, v = int(yuv[0, 0, 0]), int(yuv[0, 0, 2])
+    assert vs[255 - v, u] == 255 and np.count_nonzero(vs) == 1
+
+
+def test_alpha_rule_and_null_planes(oracle, pkg):
+    f = pkg.frames.random(31, 17, seed=1)
+    f[:, ::2, 3] = 0
+    yuv = oracle.rgb_to_yuv(f, 2)
+    assert (yuv[..., 3] == 255).all()                       # shader writes a = 1
+    assert oracle.histogram_counts(0x07, f, yuv).sum() == 3 * 17 * 15   # a == 0 skipped
+    assert oracle.histogram_counts(0x70, f, yuv).sum() == 3 * 17 * 31   # YUV plane never skipped
+    assert oracle.vectorscope(yuv).astype(int).sum() == 17 * 31         # no alpha test
+    assert oracle.histogram_counts(0x70, f, None).sum() == 0            # missing plane -> zeros
+    assert oracle.waveform(0x07, None, yuv, width=31, height=17).sum() == 0
+
+
+def test_transform_facts(oracle):
+    """facts the CUDA kernel's arithmetic relies on"""
+    for cs in (1, 2):
+        tab, clamp = oracle.rgb_to_yuv_table(cs)
+        assert not clamp, "the [0,1] clamp must never act (the kernel omits it)"
+        strict, clamp_s = oracle.rgb_to_yuv_table(cs, strict=True)
+        assert not clamp_s
+        differ = int((tab != strict).sum())
+        assert differ < 500, differ      # contracted vs no-FMA definitions: ~2e-5 of all colours
+        u, v = tab & 0xFF, tab >> 16
+        assert 15 <= u.min() and u.max() <= 239 and 16 <= v.min() and v.max() <= 240
+    assert oracle.calc_colorspace(0) == 2 and oracle.calc_colorspace(1) == 1 and oracle.calc_colorspace(7) == 2
+
+
+def test_div255_constants():
+    """x/255 == fma(x, k0, rn(x*k1)) for x in 0..255 with the constants scope_kernels.cuh uses"""
+    from fractions import Fraction
+    k0 = np.array([0x3B808081], np.uint32).view(np.float32)[0]
+    k1 = np.array([0xAF7EFEFF], np.uint32).view(np.float32)[0]
+
+    def rn32(fr):
+        f = np.float32(float(fr))
+        cands = [np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
+
+    for x in range(256):
+        ref = np.float32(x) / np.float32(255.0)
+        t = rn32(Fraction(x) * Fraction(float(k1)))
+        q = rn32(Fraction(x) * Fraction(float(k0)) + Fraction(float(t)))
+        assert q == ref, x
+
+
+def test_intensity_mapping(oracle):
+    bins = np.arange(256, dtype=np.uint8)
+    out = oracle.apply_intensity(bins, 25)
+    assert out[0] == 0 and out[10] == 250 and out[11] == 255 and (out[11:] == 255).all()
+    assert np.array_equal(oracle.apply_intensity(bins, 1), bins)

@@ -1,0 +1,109 @@
+"""Host logic of the C shim's capture core (include/cm_shim.h), no GPU: the 3-slot queue, the
+one-frame staging latency, drop-on-busy and once-per-tick rules of src/common.c."""
+import ctypes as C
+import threading
+import time
+
+import numpy as np
+import pytest
+
+
+class SurfaceData(C.Structure):
+    _fields_ = [("rgb_data", C.c_void_p), ("yuv_data", C.c_void_p), ("linesize", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("colorspace", C.c_int), ("tex", C.c_void_p)]
+
+
+CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(SurfaceData))
+
+
+@pytest.fixture()
+def shim(pkg):
+    lib = C.CDLL(pkg._ffi.SHIM_PATH)
+    lib.b200_cm_render_target.restype = C.c_bool
+    lib.b200_cm_render_target.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.b200_cm_request.argtypes = [C.c_void_p, CB, C.c_void_p]
+    for n in ("b200_cm_create", "b200_cm_destroy", "b200_cm_tick", "b200_cm_drain"):
+        getattr(lib, n).argtypes = [C.c_void_p]
+    return lib
+
+
+def _src(shim, flags=1):
+    buf = C.create_string_buffer(4096)           # opaque struct b200_cm_source
+    shim.b200_cm_create(buf)
+    # `flags` field: find it by writing through a tiny helper would need the layout; instead the
+    # tests drive flags via the documented default (0) + this poke at the known offset computed in C
+    return buf
+
+
+def test_ring_orders_frames_and_drops_when_busy(shim, pkg):
+    import struct
+    lib = shim
+    # compile-time layout probe: a tiny C helper is overkill; use offsetof via ctypes mirror
+    class Item(C.Structure):
+        _fields_ = [("staged", C.c_void_p), ("staged_bytes", C.c_size_t), ("width", C.c_uint32),
+                    ("height", C.c_uint32), ("linesize", C.c_uint32), ("flags", C.c_uint32),
+                    ("colorspace", C.c_int), ("cb", C.c_void_p), ("cb_data", C.c_void_p)]
+
+    class Cm(C.Structure):
+        _fields_ = [("queue", Item * 3), ("i_write_queue", C.c_int), ("i_staging_queue", C.c_int),
+                    ("i_read_queue", C.c_int), ("rendered", C.c_bool), ("pipeline_thread", C.c_ulong),
+                    ("pipeline_mutex", C.c_byte * 40), ("pipeline_cond", C.c_byte * 48),
+                    ("pipeline_thread_running", C.c_bool), ("request_exit", C.c_bool), ("worker_busy", C.c_bool),
+                    ("callback", C.c_void_p), ("callback_data", C.c_void_p), ("flags", C.c_uint32),
+                    ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong)]
+
+    cm = Cm()
+    lib.b200_cm_create(C.byref(cm))
+    assert (cm.i_write_queue, cm.i_staging_queue, cm.i_read_queue) == (0, 0, 2)
+    cm.flags = 1  # CONVERT_RGB
+
+    seen, gate = [], threading.Event()
+    gate.set()
+
+    def cb(_data, sd):
+        gate.wait()
+        s = sd.contents
+        first = C.cast(s.rgb_data, C.POINTER(C.c_uint8))[0]
+        seen.append((int(first), s.width, s.height, s.linesize, bool(s.yuv_data)))
+
+    cfn = CB(cb)
+    lib.b200_cm_request(C.byref(cm), cfn, None)
+    w, h = 16, 4
+
+    def frame(tag):
+        return np.full((h, w * 4), tag, np.uint8)
+
+    def render(tag):
+        f = frame(tag)
+        return lib.b200_cm_render_target(C.byref(cm), f.ctypes.data, None, w * 4, w, h)
+
+    # once per tick
+    lib.b200_cm_tick(C.byref(cm))
+    assert render(1) is True
+    assert render(99) is False
+    # the staged frame is consumed only after the NEXT one is staged (one frame of latency)
+    lib.b200_cm_drain(C.byref(cm))
+    assert seen == []
+    lib.b200_cm_tick(C.byref(cm))
+    assert render(2) is True
+    lib.b200_cm_drain(C.byref(cm))
+    assert [s[0] for s in seen] == [1]
+    assert seen[0][1:] == (w, h, w * 4, False)
+    # block the worker inside the callback, keep rendering: frames get dropped, none reordered
+    gate.clear()
+    results = []
+    for tag in range(3, 9):
+        lib.b200_cm_tick(C.byref(cm))
+        results.append(render(tag))
+        time.sleep(0.01)
+    assert results.count(False) >= 3 and cm.frames_dropped == results.count(False)
+    gate.set()
+    lib.b200_cm_tick(C.byref(cm))
+    render(50)
+    lib.b200_cm_tick(C.byref(cm))
+    render(51)
+    lib.b200_cm_drain(C.byref(cm))
+    tags = [s[0] for s in seen]
+    assert tags == sorted(tags) and tags[0] == 1 and 50 in tags
+    assert cm.frames_processed == len(seen)
+    lib.b200_cm_destroy(C.byref(cm))
