@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libscope_b200.so")
+LIB_PATH = os.environ.get("SCOPE_LIB") or os.path.join(_HERE, "lib", "libscope_b200.so")  # SCOPE_LIB: A/B builds
 SHIM_PATH = os.path.join(_HERE, "lib", "libcm_shim.so")
 
 SCOPE_OK = 0

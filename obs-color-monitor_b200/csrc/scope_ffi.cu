@@ -56,11 +56,15 @@ struct scope_ctx {
 	std::string err;
 	uint64_t launches = 0;
 	PFN_encodeTiled encode = nullptr;
+	bool default_tma = true; // which loader launch_strip prefers when both are possible
 	// scratch u32 vectorscope accumulators [n][65536]
 	uint32_t *d_vs_acc = nullptr;
 	size_t vs_acc_frames = 0;
 	uint32_t *d_hist_scratch = nullptr;
 	size_t hist_scratch_frames = 0;
+	// work counters of the dynamically scheduled launches (one slot per launch, round robin)
+	uint32_t *d_counters = nullptr;
+	uint32_t counter_next = 0;
 	RingSlot ring[SCOPE_RING_SLOTS];
 	std::mutex mu;
 	// optional per-launch timing of the strip kernel (scope_profile_*)
@@ -116,38 +120,50 @@ void decode_components(uint32_t comp, int &src, uint32_t &mask)
 		mask = 0;
 }
 
-typedef void (*StripKernel)(const StripParams, const CUtensorMap, const CUtensorMap);
+typedef void (*TmaKernel)(const StripParams, const CUtensorMap, const CUtensorMap);
+typedef void (*LdgKernel)(const StripParams);
 
-template <int SRC, bool VS, bool SURF, bool TMA>
-void kernel_entry(StripKernel &fn, int &smem)
+struct KernelChoice {
+	TmaKernel tma = nullptr;
+	LdgKernel ldg = nullptr;
+	int smem = 0, threads = 0;
+};
+
+template <int SRC, bool VS, bool SURF>
+void kernel_entry(bool tma, KernelChoice &k)
 {
-	fn = scope_strip_kernel<SRC, VS, SURF, TMA>;
-	smem = SmemLayout<SRC, VS, SURF, TMA>::kTotal;
+	if (tma) {
+		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
+		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
+		k.threads = kTmaWarps * 32 + 32;
+	} else {
+		k.ldg = scope_strip_kernel_ldg<SRC, VS, SURF>;
+		k.smem = SmemLayout<SRC, VS, SURF, false>::kTotal;
+		k.threads = kLdgWarps * 32;
+	}
 }
 
-template <bool SURF, bool TMA>
-bool pick_kernel2(int src, bool vs, StripKernel &fn, int &smem)
+template <bool SURF>
+bool pick_kernel2(int src, bool vs, bool tma, KernelChoice &k)
 {
 	if (src == SRC_NONE && vs)
-		kernel_entry<SRC_NONE, true, SURF, TMA>(fn, smem);
+		kernel_entry<SRC_NONE, true, SURF>(tma, k);
 	else if (src == SRC_RGB && vs)
-		kernel_entry<SRC_RGB, true, SURF, TMA>(fn, smem);
+		kernel_entry<SRC_RGB, true, SURF>(tma, k);
 	else if (src == SRC_RGB && !vs)
-		kernel_entry<SRC_RGB, false, SURF, TMA>(fn, smem);
+		kernel_entry<SRC_RGB, false, SURF>(tma, k);
 	else if (src == SRC_YUV && vs)
-		kernel_entry<SRC_YUV, true, SURF, TMA>(fn, smem);
+		kernel_entry<SRC_YUV, true, SURF>(tma, k);
 	else if (src == SRC_YUV && !vs)
-		kernel_entry<SRC_YUV, false, SURF, TMA>(fn, smem);
+		kernel_entry<SRC_YUV, false, SURF>(tma, k);
 	else
 		return false;
 	return true;
 }
 
-bool pick_kernel(int src, bool vs, bool surface, bool tma, StripKernel &fn, int &smem)
+bool pick_kernel(int src, bool vs, bool surface, bool tma, KernelChoice &k)
 {
-	if (surface)
-		return tma ? pick_kernel2<true, true>(src, vs, fn, smem) : pick_kernel2<true, false>(src, vs, fn, smem);
-	return tma ? pick_kernel2<false, true>(src, vs, fn, smem) : pick_kernel2<false, false>(src, vs, fn, smem);
+	return surface ? pick_kernel2<true>(src, vs, tma, k) : pick_kernel2<false>(src, vs, tma, k);
 }
 
 int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x_extent_px, uint32_t linesize,
@@ -229,50 +245,62 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	P.vscope_stride = rq.vs_stride;
 	P.coef = coef_for(rq.colorspace);
 
-	// TMA needs 16-byte pitches; the base may be 4-byte aligned (handled by an x offset)
-	const bool strides_ok = (rq.linesize % 16u) == 0 && (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0);
-	const bool same_mis = !(need_rgb && need_yuv) || (((uintptr_t)rq.rgb & 15u) == ((uintptr_t)rq.yuv & 15u));
-	// SCOPE_DISABLE_TMA=1 forces the plain-load kernels (debugging / A-B measurements)
-	const char *no_tma = getenv("SCOPE_DISABLE_TMA");
-	const bool use_tma = ctx->encode != nullptr && strides_ok && same_mis && !(no_tma && no_tma[0] == '1');
+	// Loader choice.  TMA can describe the planes only if base pointers, pitch and frame
+	// stride are multiples of 16 bytes; everything else takes the direct loader.
+	// SCOPE_LOADER=tma|ldg overrides the default (see DESIGN.md section 4.4 for the measurements).
+	const bool tma_ok = ctx->encode != nullptr && (rq.linesize % 16u) == 0 &&
+			    (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0) &&
+			    (!need_rgb || ((uintptr_t)rq.rgb & 15u) == 0) && (!need_yuv || ((uintptr_t)rq.yuv & 15u) == 0);
+	const char *loader = getenv("SCOPE_LOADER");
+	bool use_tma = tma_ok && ctx->default_tma;
+	if (loader && !strcmp(loader, "tma"))
+		use_tma = tma_ok;
+	else if (loader && !strcmp(loader, "ldg"))
+		use_tma = false;
 
 	CUtensorMap map_rgb, map_yuv;
 	memset(&map_rgb, 0, sizeof map_rgb);
 	memset(&map_yuv, 0, sizeof map_yuv);
 	if (use_tma) {
-		const uint8_t *any = need_rgb ? rq.rgb : rq.yuv;
-		const uint32_t mis_px = (uint32_t)(((uintptr_t)any & 15u) / 4u);
-		P.tma_x0 = mis_px;
 		if (need_rgb) {
-			int r = make_map(ctx, &map_rgb, rq.rgb - mis_px * 4, mis_px + rq.width, rq.linesize, rq.height,
-					 rq.n_frames, rq.frame_stride);
+			int r = make_map(ctx, &map_rgb, rq.rgb, rq.width, rq.linesize, rq.height, rq.n_frames, rq.frame_stride);
 			if (r)
 				return r;
 		}
 		if (need_yuv) {
-			int r = make_map(ctx, &map_yuv, rq.yuv - mis_px * 4, mis_px + rq.width, rq.linesize, rq.height,
-					 rq.n_frames, rq.frame_stride);
+			int r = make_map(ctx, &map_yuv, rq.yuv, rq.width, rq.linesize, rq.height, rq.n_frames, rq.frame_stride);
 			if (r)
 				return r;
 		}
 	}
 
-	StripKernel fn = nullptr;
-	int smem = 0;
-	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, fn, smem))
+	KernelChoice k;
+	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, k))
 		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
-	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	const void *fn = use_tma ? (const void *)k.tma : (const void *)k.ldg;
+	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
 
 	int ctas_per_sm = 1;
-	const int threads = kConsumerThreads + (use_tma ? 32 : 0);
-	CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, threads, smem));
+	CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, k.threads, k.smem));
 	if (ctas_per_sm < 1)
 		return fail(ctx, SCOPE_ERR_CUDA, "kernel does not fit on an SM");
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
 	if (grid > P.items)
 		grid = P.items;
-	P.items_per_cta = (P.items + grid - 1) / grid;
-	grid = (P.items + P.items_per_cta - 1) / P.items_per_cta;
+	if (use_tma) {
+		// chunks of kChunkItems strips are claimed at run time from a zeroed counter
+		const uint32_t n_chunks = (P.items + kChunkItems - 1) / kChunkItems;
+		if (grid > n_chunks)
+			grid = n_chunks;
+		if (!ctx->d_counters)
+			CU_TRY(ctx, cudaMalloc(&ctx->d_counters, 256 * sizeof(uint32_t)));
+		P.chunk_counter = ctx->d_counters + (ctx->counter_next++ & 255u);
+		CU_TRY(ctx, cudaMemsetAsync(P.chunk_counter, 0, sizeof(uint32_t), stream));
+		P.items_per_cta = 0;
+	} else {
+		P.items_per_cta = (P.items + grid - 1) / grid;
+		grid = (P.items + P.items_per_cta - 1) / P.items_per_cta;
+	}
 
 	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
 	if (ctx->profiling) {
@@ -285,7 +313,10 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 		}
 		CU_TRY(ctx, cudaEventRecord(ev.first, stream));
 	}
-	fn<<<grid, threads, smem, stream>>>(P, map_rgb, map_yuv);
+	if (use_tma)
+		k.tma<<<grid, k.threads, k.smem, stream>>>(P, map_rgb, map_yuv);
+	else
+		k.ldg<<<grid, k.threads, k.smem, stream>>>(P);
 	CU_TRY(ctx, cudaGetLastError());
 	if (ctx->profiling) {
 		CU_TRY(ctx, cudaEventRecord(ev.second, stream));
@@ -750,6 +781,7 @@ void scope_ctx_destroy(scope_ctx *ctx)
 	}
 	cudaFree(ctx->d_vs_acc);
 	cudaFree(ctx->d_hist_scratch);
+	cudaFree(ctx->d_counters);
 	for (auto &ev : ctx->prof_events)
 		ctx->prof_pool.push_back(ev);
 	for (auto &ev : ctx->prof_pool) {

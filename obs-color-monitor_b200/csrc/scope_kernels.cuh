@@ -13,8 +13,9 @@
 //     atomics by construction, and no two lanes of a warp ever share an address;
 //   - the CTA owns its 32 output columns exclusively and writes the final saturated
 //     u8 waveform directly (no zero-fill pass, no global atomics for the waveform).
-// Pixels arrive through TMA (cp.async.bulk.tensor) into a 4-stage shared-memory ring
-// filled by a producer warp; consumers read one 32-bit pixel per lane per row.
+// Pixels arrive through TMA (cp.async.bulk.tensor) into a 4-stage shared-memory ring filled
+// by a producer warp; consumers read one 32-bit pixel per lane per row.  A plain-load kernel
+// covers planes TMA cannot describe.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -23,12 +24,14 @@
 namespace scope {
 
 constexpr int kStripPx = 32;          // columns per strip == lanes per warp
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kTileRows = 64;         // rows per TMA stage (4 rows per consumer warp)
-constexpr int kRowsPerWarp = kTileRows / kConsumerWarps;
-constexpr int kStages = 4;
+constexpr int kTileRows = 64;         // rows per TMA tile
+constexpr int kTmaWarps = 16;         // consumer warps of the TMA kernel (4 rows of each tile per warp)
+constexpr int kMaxStages = 4;         // depth of the tile ring (what the bins leave room for)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
+constexpr int kChunkItems = 10;       // strips per dynamically claimed chunk
+constexpr int kQueue = 4;             // chunk-id mailbox entries (producer is < kQueue chunks ahead)
+constexpr int kLdgWarps = 16;              // plain-load fallback kernel
+constexpr int kLdgRows = 4;
 constexpr int kVsWords = 32768;       // 65536 vectorscope bins, two u16 per word
 constexpr int kWaveWords = 256 * 32;  // one plane: [level][lane]
 
@@ -52,7 +55,7 @@ struct StripParams {
 	uint32_t x_offset;        // first output column (tile-sharded frames)
 	uint32_t out_width;       // row length of the waveform output in pixels
 	uint32_t partial;         // 1: add u16 pairs into wave_pairs instead of writing u8
-	uint32_t tma_x0;          // pixel offset of column 0 inside the tensor map
+	uint32_t *chunk_counter;  // global work counter of this launch (zeroed by the host)
 	uint32_t *hist;           // [n][1024] u32, zeroed
 	uint8_t *wave;            // [n][256][out_width][4]
 	uint32_t *wave_pairs;     // partial: [256][out_width][2]
@@ -86,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 	asm volatile("{\n"
 		     ".reg .pred p;\n"
 		     "WAIT_%=:\n"
-		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
 		     "@p bra DONE_%=;\n"
 		     "bra WAIT_%=;\n"
 		     "DONE_%=:\n"
@@ -99,21 +102,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
 		     " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
 		     "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
-		     : "memory");
-}
-__device__ __forceinline__ void consumer_bar()
-{
-	asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-}
-// predicated shared-memory reduction: no branch, no return value
-__device__ __forceinline__ void red_shared_if(uint32_t addr, uint32_t val, bool pred)
-{
-	asm volatile("{\n"
-		     ".reg .pred p;\n"
-		     "setp.ne.u32 p, %2, 0;\n"
-		     "@p red.shared.add.u32 [%0], %1;\n"
-		     "}" ::"r"(addr),
-		     "r"(val), "r"((uint32_t)pred)
 		     : "memory");
 }
 __device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t val)
@@ -170,19 +158,35 @@ __device__ __forceinline__ f32x2 splat2(float c)
 	return pack2(c, c);
 }
 
-// byte k of the two pixels -> exact floats (2^23 + b, then - 2^23)
+// ---------------------------------------------------------------------------
+// "carriers": a byte b travels as the bit pattern 0x4B0000bb, i.e. the float 2^23 + b.
+//   * PRMT makes one from a pixel byte in a single instruction;
+//   * the colour transform ends in such a pattern (add.rz with 2^23);
+//   * (carrier << 7) + (base - 0x80000000) == base + 128*b   (0x4B000000 << 7 = 0x80000000
+//     mod 2^32), so a waveform bin address is ONE multiply-add away from a carrier.
+// ---------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ f32x2 bytes_to_f32x2(uint32_t pa, uint32_t pb)
+__device__ __forceinline__ uint32_t carrier(uint32_t pixel, uint32_t magic)
 {
-	const uint32_t magic = 0x4B000000u; // 8388608.0f
-	const uint32_t fa = __byte_perm(pa, magic, 0x7650 + K);
-	const uint32_t fb = __byte_perm(pb, magic, 0x7650 + K);
-	return add2(pack2(__uint_as_float(fa), __uint_as_float(fb)), splat2(-8388608.0f));
+	uint32_t r;
+	if (K == 0)
+		asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(pixel), "r"(magic));
+	else if (K == 1)
+		asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(pixel), "r"(magic));
+	else
+		asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(pixel), "r"(magic));
+	return r;
+}
+
+// carriers of two pixels -> exact floats b (subtract 2^23), packed
+__device__ __forceinline__ f32x2 carriers_to_f32x2(uint32_t ca, uint32_t cb)
+{
+	return add2(pack2(__uint_as_float(ca), __uint_as_float(cb)), splat2(-8388608.0f));
 }
 
 // x / 255 correctly rounded for x in {0..255}: fma(x, k0, rn(x*k1)), k0 = rn(1/255),
 // k1 = rn(1/255 - k0).  Checked against IEEE division for all 256 inputs
-// (tests/test_transform_math.py) and, through the kernel, for all 2^24 colours.
+// (tests/test_oracle.py::test_div255_constants) and, through the kernel, for all 2^24 colours.
 __device__ __forceinline__ f32x2 div255(f32x2 x)
 {
 	const f32x2 k0 = splat2(__uint_as_float(0x3B808081u)); // 0x1.010102p-8
@@ -191,41 +195,32 @@ __device__ __forceinline__ f32x2 div255(f32x2 x)
 }
 
 // one output channel for two pixels: p = c0*r; p = fma(c1,g,p); p = fma(c2,b,p); t = p + off;
-// q = floor(fma(t, 255, 0.5)).  Returns the two floats 2^23 + q (low byte of the bit
-// pattern = q).  The [0,1] clamp of the definition never acts (exhaustively verified).
-__device__ __forceinline__ f32x2 yuv_channel(f32x2 r, f32x2 g, f32x2 b, float c0, float c1, float c2, float off)
+// q = floor(fma(t, 255, 0.5)).  Returns the two CARRIERS of q (floats 2^23 + q).  The [0,1]
+// clamp of the definition never acts (exhaustively verified, tests/test_oracle.py).
+__device__ __forceinline__ void yuv_channel(f32x2 r, f32x2 g, f32x2 b, float c0, float c1, float c2, float off,
+					    uint32_t &qa, uint32_t &qb)
 {
 	f32x2 p = mul2(splat2(c0), r);
 	p = fma2(splat2(c1), g, p);
 	p = fma2(splat2(c2), b, p);
 	p = add2(p, splat2(off));
 	p = fma2(p, splat2(255.0f), splat2(0.5f));
-	return add2_rz(p, splat2(8388608.0f));
+	unpack2(add2_rz(p, splat2(8388608.0f)), qa, qb);
 }
 
-// BGRA pixel pair -> [U,Y,V,255] pixel pair (data/common.effect:23-43 as pinned in
-// oracle/scope_oracle.c).  NEED_Y = false leaves the Y byte 0 (vectorscope only).
+// RGB carriers of two pixels -> U/(Y)/V carriers (data/common.effect:23-43 as pinned in
+// oracle/scope_oracle.c).
 template <bool NEED_Y>
-__device__ __forceinline__ void rgb_to_yuv_pair(uint32_t pa, uint32_t pb, const Coef &c, uint32_t &qa, uint32_t &qb)
+__device__ __forceinline__ void rgb_to_yuv_pair(const uint32_t (&ca)[3], const uint32_t (&cb)[3], const Coef &c,
+						 uint32_t (&ya)[3], uint32_t (&yb)[3])
 {
-	const f32x2 b = div255(bytes_to_f32x2<0>(pa, pb));
-	const f32x2 g = div255(bytes_to_f32x2<1>(pa, pb));
-	const f32x2 r = div255(bytes_to_f32x2<2>(pa, pb));
-	uint32_t ua, ub, va, vb;
-	unpack2(yuv_channel(r, g, b, c.u0, c.u1, c.u2, 0.5f - 1.0f / 256.0f), ua, ub);
-	unpack2(yuv_channel(r, g, b, c.v0, c.v1, c.v2, 0.5f), va, vb);
-	if (NEED_Y) {
-		uint32_t ya, yb;
-		unpack2(yuv_channel(r, g, b, c.y0, c.y1, c.y2, 0.0f), ya, yb);
-		// byte0 = u.b0, byte1 = y.b0 ; then byte2 = v.b0, byte3 = 0xFF
-		const uint32_t ta = __byte_perm(ua, ya, 0x0040), tb = __byte_perm(ub, yb, 0x0040);
-		qa = __byte_perm(ta, va | 0xFF00u, 0x5410);
-		qb = __byte_perm(tb, vb | 0xFF00u, 0x5410);
-	} else {
-		// 0x4B0000vv has zero bytes 1,2: byte0 = u.b0, byte1 = 0, byte2 = v.b0, byte3 = 0xFF
-		qa = __byte_perm(ua, va | 0xFF00u, 0x5420);
-		qb = __byte_perm(ub, vb | 0xFF00u, 0x5420);
-	}
+	const f32x2 b = div255(carriers_to_f32x2(ca[0], cb[0]));
+	const f32x2 g = div255(carriers_to_f32x2(ca[1], cb[1]));
+	const f32x2 r = div255(carriers_to_f32x2(ca[2], cb[2]));
+	yuv_channel(r, g, b, c.u0, c.u1, c.u2, 0.5f - 1.0f / 256.0f, ya[0], yb[0]);
+	if (NEED_Y)
+		yuv_channel(r, g, b, c.y0, c.y1, c.y2, 0.0f, ya[1], yb[1]);
+	yuv_channel(r, g, b, c.v0, c.v1, c.v2, 0.5f, ya[2], yb[2]);
 }
 
 // ---------------------------------------------------------------------------
@@ -242,107 +237,358 @@ struct SmemLayout {
 	static constexpr int kWaveBytes = SRC != SRC_NONE ? 2 * kWaveWords * 4 : 0;
 	static constexpr int kStageOff = kWave0Off + kWaveBytes;
 	static constexpr int kStageBytes = USE_TMA ? kPlanes * kTileBytes : 0;
+	// two planes per stage (surface mode) leave room for a 2-deep ring only
+	static constexpr int kStages = kPlanes == 2 ? 2 : kMaxStages;
 	static constexpr int kBarOff = kStageOff + kStages * kStageBytes;
-	static constexpr int kTotal = kBarOff + (USE_TMA ? 2 * kStages * 8 : 0) + 16;
+	static constexpr int kQueueOff = kBarOff + (USE_TMA ? 2 * kMaxStages * 8 : 0);
+	static constexpr int kTotal = kQueueOff + (USE_TMA ? kQueue * 4 : 0) + 16;
 };
 
 // ---------------------------------------------------------------------------
-// per-pixel accumulation
+// per-pixel accumulation primitives
 // ---------------------------------------------------------------------------
-// waveform/histogram column bins.  plane0[level][lane] = (count B|U : lo16, count G|Y : hi16),
+__device__ __forceinline__ void red_shared(uint32_t addr, uint32_t val)
+{
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+}
+
+// Waveform / histogram column bins: plane0[level][lane] = (count B|U : lo16, count G|Y : hi16),
 // plane1[level][lane] = (count R|V : lo16).  A strip has <= 65535 rows, so no half overflows.
-__device__ __forceinline__ void bins_add(uint32_t s, uint32_t wave_lane_addr, bool ok, uint32_t mask)
+// wb0 / wb1 = lane's plane-0 / plane-1 base address minus 0x80000000 (see "carriers").
+// `one` is 1 for a counted pixel and 0 for a skipped one (alpha == 0: histogram.c:385-387,
+// waveform.c:246-248; or outside the frame): adding 0 needs no predication and no branch.
+template <bool DO_B, bool DO_G, bool DO_R>
+__device__ __forceinline__ void bins_add(uint32_t cb, uint32_t cg, uint32_t cr, uint32_t wb0, uint32_t wb1,
+					 uint32_t one)
 {
-	ok = ok && (s > 0x00FFFFFFu); // alpha != 0 (histogram.c:385-387, waveform.c:246-248)
-	const uint32_t ab = wave_lane_addr + ((s & 0xFFu) << 7);
-	const uint32_t ag = wave_lane_addr + ((s >> 1) & 0x7F80u);
-	const uint32_t ar = wave_lane_addr + kWaveWords * 4 + ((s >> 9) & 0x7F80u);
-	red_shared_if(ab, 1u, ok && (mask & 1u));
-	red_shared_if(ag, 0x10000u, ok && (mask & 2u));
-	red_shared_if(ar, 1u, ok && (mask & 4u));
+	if (DO_B)
+		red_shared(cb * 128u + wb0, one);
+	if (DO_G)
+		red_shared(cg * 128u + wb0, one << 16);
+	if (DO_R)
+		red_shared(cr * 128u + wb1, one);
 }
 
-// vectorscope bin index of a [U,Y,V,A] pixel: row = 255 - V, column = U (vectorscope.c:232)
-__device__ __forceinline__ uint32_t vs_index(uint32_t q)
+// Vectorscope bins in shared memory are indexed by idx = U | V << 8 (NOT yet flipped to the
+// reference's row = 255 - V; the flush does that) and are u16 halves, two per 32-bit word:
+// word = idx & 0x7FFF, half = V >> 7.  vs_add returns the bit of the OLD word that says "this
+// half already held >= 0x8000"; the caller ORs those over its pixels and, only if any is set,
+// calls vs_undo.  An add that found its bin at >= 0x8000 is taken back, so a half can never
+// wrap 16 bits, and a bin that ever reached 0x8000 keeps a value far above 255: it saturates
+// to 255 at the end exactly like the reference's `if (*c < 255) ++*c`.
+struct VsAdd {
+	uint32_t addr, add, sat;
+};
+__device__ __forceinline__ VsAdd vs_add(uint32_t vs_base, uint32_t idx, uint32_t k)
 {
-	return __byte_perm(q, ~q, 0x4460) & 0xFFFFu; // byte0 = q.b0 (U), byte1 = (~q).b2 (255-V)
+	VsAdd r;
+	r.addr = (idx & 0x7FFFu) * 4u + vs_base;
+	r.add = (idx >> 15) * (k * 0xFFFFu) + k; // k << 16 for the upper half, k for the lower
+	const uint32_t old = atom_shared_add(r.addr, r.add);
+	r.sat = old & ((idx >> 15) * 0x7FFF8000u + 0x8000u);
+	return r;
 }
-
-// add `k` to bin idx (u16 halves, two bins per word).  When a half crosses 0x8000 the
-// add that crossed subtracts 0x4000 again: the bin stays > 255 (it saturates to 255 at
-// the end, like the reference's `if (*c < 255) ++*c`) and can never wrap 16 bits.
-__device__ __forceinline__ void vs_add(uint32_t vs_base, uint32_t idx, uint32_t k)
+__device__ __forceinline__ void vs_undo(const VsAdd &a)
 {
-	const uint32_t addr = vs_base + ((idx << 1) & ~3u);
-	const uint32_t sh = (idx & 1u) << 4;
-	const uint32_t add = k << sh;
-	const uint32_t old = atom_shared_add(addr, add);
-	if (((old ^ (old + add)) & (0x8000u << sh)) != 0u)
-		atom_shared_add(addr, 0u - (0x4000u << sh));
+	if (a.sat)
+		red_shared(a.addr, 0u - a.add);
 }
 
 // ---------------------------------------------------------------------------
-// the strip kernel
+// one thread's share of a tile: N vertically adjacent pixels of its column.
+// FAST = the tile lies completely inside the frame and all three channels are accumulated:
+// no per-pixel validity logic at all.
 // ---------------------------------------------------------------------------
-template <int SRC, bool VSCOPE, bool SURFACE, bool USE_TMA>
-__global__ void __launch_bounds__(kConsumerThreads + (USE_TMA ? 32 : 0), 1)
-	scope_strip_kernel(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
-			   const __grid_constant__ CUtensorMap map_yuv)
+struct TileCtx {
+	uint32_t vs_base, wb0, wb1, magic, bins_mask;
+	int lane;
+};
+
+template <int SRC, bool VSCOPE, bool SURFACE, bool FAST, int N>
+__device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef, const uint32_t (&p)[N],
+					     const uint32_t (&q)[N], const bool (&ok)[N])
 {
-	using L = SmemLayout<SRC, VSCOPE, SURFACE, USE_TMA>;
+	static_assert(N % 2 == 0, "pixels are transformed in packed pairs");
+	constexpr bool kTransform = !SURFACE && (VSCOPE || SRC == SRC_YUV);
+	uint32_t crgb[N][3]; // carriers of B, G, R
+	uint32_t cyuv[N][3]; // carriers of U, Y, V
+	if (SRC == SRC_RGB || kTransform) {
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			crgb[k][0] = carrier<0>(p[k], c.magic);
+			crgb[k][1] = carrier<1>(p[k], c.magic);
+			crgb[k][2] = carrier<2>(p[k], c.magic);
+		}
+	}
+	if (kTransform) {
+#pragma unroll
+		for (int k = 0; k < N; k += 2)
+			rgb_to_yuv_pair<SRC == SRC_YUV>(crgb[k], crgb[k + 1], coef, cyuv[k], cyuv[k + 1]);
+	} else if (SURFACE && SRC == SRC_YUV) {
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			cyuv[k][0] = carrier<0>(q[k], c.magic);
+			cyuv[k][1] = carrier<1>(q[k], c.magic);
+			cyuv[k][2] = carrier<2>(q[k], c.magic);
+		}
+	}
+
+	// ---- waveform / histogram column bins ----
+	if (SRC != SRC_NONE) {
+		const uint32_t(*cs)[3] = SRC == SRC_RGB ? crgb : cyuv;
+		// the word whose alpha byte decides whether a pixel counts (the fused YUV plane has
+		// alpha 255 everywhere, common.effect:30,41); pixels outside the frame arrive as 0
+		bool all_counted;
+		if (SRC == SRC_RGB || SURFACE) {
+			const uint32_t *a = SRC == SRC_RGB ? p : q;
+			uint32_t m = a[0];
+#pragma unroll
+			for (int k = 1; k < N; k++)
+				m = min(m, a[k]);
+			all_counted = m > 0x00FFFFFFu;
+		} else {
+			all_counted = FAST || (ok[0] && ok[N - 1]);
+		}
+		if ((FAST || c.bins_mask == 7u) && __all_sync(0xFFFFFFFFu, all_counted)) {
+#pragma unroll
+			for (int k = 0; k < N; k++)
+				bins_add<true, true, true>(cs[k][0], cs[k][1], cs[k][2], c.wb0, c.wb1, 1u);
+		} else {
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				uint32_t one;
+				if (SRC == SRC_RGB)
+					one = p[k] > 0x00FFFFFFu ? 1u : 0u;
+				else if (SURFACE)
+					one = q[k] > 0x00FFFFFFu ? 1u : 0u;
+				else
+					one = ok[k] ? 1u : 0u;
+				if (FAST || (c.bins_mask & 1u))
+					bins_add<true, false, false>(cs[k][0], cs[k][1], cs[k][2], c.wb0, c.wb1, one);
+				if (FAST || (c.bins_mask & 2u))
+					bins_add<false, true, false>(cs[k][0], cs[k][1], cs[k][2], c.wb0, c.wb1, one);
+				if (FAST || (c.bins_mask & 4u))
+					bins_add<false, false, true>(cs[k][0], cs[k][1], cs[k][2], c.wb0, c.wb1, one);
+			}
+		}
+	}
+
+	// ---- vectorscope ----
+	if (VSCOPE) {
+		uint32_t idx[N]; // U | V << 8
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			if (SURFACE)
+				idx[k] = __byte_perm(q[k], 0u, 0x4420);
+			else
+				idx[k] = __byte_perm(cyuv[k][0], cyuv[k][2], 0x1140);
+		}
+		const bool full = FAST || (ok[0] && ok[N - 1]); // this lane's N pixels all valid
+		bool same = full;
+#pragma unroll
+		for (int k = 1; k < N; k++)
+			same = same && (idx[k] == idx[0]);
+		// (the shuffle must be executed by every lane: no short-circuit around it)
+		const uint32_t idx_lane0 = __shfl_sync(0xFFFFFFFFu, idx[0], 0);
+		same = same && (idx[0] == idx_lane0);
+		if (__all_sync(0xFFFFFFFFu, same)) {
+			// flat block: all N x 32 pixels hit one bin -> one atomic
+			if (c.lane == 0)
+				vs_undo(vs_add(c.vs_base, idx[0], 32u * N));
+		} else if (FAST) {
+			// N adds in flight, one combined overflow check
+			VsAdd a[N];
+			uint32_t any = 0;
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				a[k] = vs_add(c.vs_base, idx[k], 1u);
+				any |= a[k].sat;
+			}
+			if (any) {
+#pragma unroll
+				for (int k = 0; k < N; k++)
+					vs_undo(a[k]);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < N; k++)
+				if (ok[k])
+					vs_undo(vs_add(c.vs_base, idx[k], 1u));
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// pieces shared by the two strip kernels (NW = accumulating warps per CTA)
+// ---------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void workers_bar()
+{
+	asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+}
+
+template <int NW>
+__device__ __forceinline__ void zero_bins(uint32_t *vs, uint32_t *wave0, bool vscope, bool bins, int tid)
+{
+	if (vscope)
+		for (int i = tid; i < kVsWords / 4; i += NW * 32)
+			reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
+	if (bins)
+		for (int i = tid; i < 2 * kWaveWords / 4; i += NW * 32)
+			reinterpret_cast<uint4 *>(wave0)[i] = make_uint4(0, 0, 0, 0);
+}
+
+// every worker thread: move its slice of the u16 pairs to the frame's u32 accumulators,
+// flipping V into the reference's row order (row = 255 - V, vectorscope.c:232)
+template <int NW>
+__device__ __forceinline__ void flush_vscope(const StripParams &P, uint32_t *vs, uint32_t frame, int tid)
+{
+	workers_bar<NW>();
+	uint32_t *acc = P.vscope_acc + (size_t)frame * P.vscope_stride;
+	for (int i = tid; i < kVsWords / 4; i += NW * 32) {
+		uint4 w = reinterpret_cast<uint4 *>(vs)[i];
+		if ((w.x | w.y | w.z | w.w) != 0u) {
+			const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+			const uint32_t word = i * 4; // = U | (V & 0x7F) << 8
+			const uint32_t u = word & 0xFFu, v7 = word >> 8;
+			uint32_t *lo = acc + (255u - v7) * 256u + u; // V = v7
+			uint32_t *hi = acc + (127u - v7) * 256u + u; // V = v7 | 0x80
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (ww[j] & 0xFFFFu)
+					atomicAdd(lo + j, ww[j] & 0xFFFFu);
+				if (ww[j] >> 16)
+					atomicAdd(hi + j, ww[j] >> 16);
+			}
+			reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
+		}
+	}
+	workers_bar<NW>();
+}
+
+// end of a strip: write this strip's 32 waveform columns (final, saturated) and add the
+// strip's share of the histogram (= column bins summed over the 32 columns); re-zero the bins
+template <int NW>
+__device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0, uint32_t frame, uint32_t x,
+					   bool lane_ok, int warp, int lane)
+{
+	workers_bar<NW>();
+	uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
+	const uint32_t xo = P.x_offset + x;
+	for (int v = warp; v < 256; v += NW) {
+		const uint32_t w0 = wave0[v * 32 + lane];
+		const uint32_t w1 = wave0[kWaveWords + v * 32 + lane];
+		wave0[v * 32 + lane] = 0;
+		wave0[kWaveWords + v * 32 + lane] = 0;
+		const uint32_t cb = w0 & 0xFFFFu, cg = w0 >> 16, cr = w1 & 0xFFFFu;
+		if (P.hist_mask) {
+			const uint32_t sb = __reduce_add_sync(0xFFFFFFFFu, cb);
+			const uint32_t sg = __reduce_add_sync(0xFFFFFFFFu, cg);
+			const uint32_t sr = __reduce_add_sync(0xFFFFFFFFu, cr);
+			if (lane == 0) {
+				if ((P.hist_mask & 4u) && sr)
+					atomicAdd(hist + v * 4 + 0, sr);
+				if ((P.hist_mask & 2u) && sg)
+					atomicAdd(hist + v * 4 + 1, sg);
+				if ((P.hist_mask & 1u) && sb)
+					atomicAdd(hist + v * 4 + 2, sb);
+			}
+		}
+		if (P.wave_mask && lane_ok) {
+			const uint32_t mb = (P.wave_mask & 1u) ? cb : 0u;
+			const uint32_t mg = (P.wave_mask & 2u) ? cg : 0u;
+			const uint32_t mr = (P.wave_mask & 4u) ? cr : 0u;
+			const size_t o = (size_t)(255 - v) * P.out_width + xo;
+			if (P.partial) {
+				if (mb | mg)
+					atomicAdd(P.wave_pairs + o * 2, mb | (mg << 16));
+				if (mr)
+					atomicAdd(P.wave_pairs + o * 2 + 1, mr);
+			} else {
+				uint32_t *dst = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride);
+				dst[o] = min(mb, 255u) | (min(mg, 255u) << 8) | (min(mr, 255u) << 16);
+			}
+		}
+	}
+	workers_bar<NW>();
+}
+
+// ---------------------------------------------------------------------------
+// strip kernel, TMA loader.  A producer warp (one elected lane) walks CHUNKS of kChunkItems
+// consecutive strips, claimed from a global counter so that fast and slow frame content
+// balances across CTAs, and fills a kStages-deep shared-memory ring of 64-row x 128-byte
+// tiles with cp.async.bulk.tensor.  16 consumer warps take 4 rows of every tile each.
+// The chunk id travels to the consumers through a small shared-memory queue that is written
+// before the chunk's first tile is armed (mbarrier release/acquire orders it).
+// ---------------------------------------------------------------------------
+template <int SRC, bool VSCOPE, bool SURFACE>
+__global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
+	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
+			       const __grid_constant__ CUtensorMap map_yuv)
+{
+	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
+	constexpr int NW = kTmaWarps, RPW = kTileRows / NW;
+	constexpr int kStages = L::kStages;
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
 	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
+	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff); // kQueue entries
 	const uint32_t smem_base = smem_u32(smem);
-	const uint32_t bar_full = smem_base + L::kBarOff;          // kStages x 8 B
-	const uint32_t bar_empty = bar_full + kStages * 8;         // kStages x 8 B
+	const uint32_t bar_full = smem_base + L::kBarOff;     // kStages x 8 B
+	const uint32_t bar_empty = bar_full + kMaxStages * 8; // kStages x 8 B
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
-	const bool is_producer = USE_TMA && warp == kConsumerWarps;
+	const bool is_producer = warp == NW;
 
-	// ---- one-time setup: zero the bins, init barriers ----
-	if (!is_producer) {
-		if (VSCOPE)
-			for (int i = tid; i < kVsWords / 4; i += kConsumerThreads)
-				reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
-		if (SRC != SRC_NONE)
-			for (int i = tid; i < 2 * kWaveWords / 4; i += kConsumerThreads)
-				reinterpret_cast<uint4 *>(wave0)[i] = make_uint4(0, 0, 0, 0);
-	}
-	if (USE_TMA && tid == 0) {
+	if (!is_producer)
+		zero_bins<NW>(vs, wave0, VSCOPE, SRC != SRC_NONE, tid);
+	if (tid == 0) {
 		for (int s = 0; s < kStages; s++) {
 			mbar_init(bar_full + 8 * s, 1);
-			mbar_init(bar_empty + 8 * s, kConsumerWarps);
+			mbar_init(bar_empty + 8 * s, NW);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	const uint32_t first = blockIdx.x * P.items_per_cta;
-	const uint32_t last = min(first + P.items_per_cta, P.items);
 	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
+	const uint32_t n_chunks = (P.items + kChunkItems - 1) / kChunkItems;
 
 	if (is_producer) {
 		// ================= TMA producer (one elected lane) =================
 		if (lane == 0) {
-			uint32_t stage = 0, phase = 0;
-			for (uint32_t item = first; item < last; item++) {
-				const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
-				const int x = (int)(P.tma_x0 + strip * kStripPx);
-				for (uint32_t t = 0; t < tiles; t++) {
-					mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-					const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
-					mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
-					if (L::kLoadRgb)
-						tma_load_3d(dst, &map_rgb, bar_full + 8 * stage, x, (int)(t * kTileRows),
-							    (int)frame);
-					if (L::kLoadYuv)
-						tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), &map_yuv,
-							    bar_full + 8 * stage, x, (int)(t * kTileRows), (int)frame);
-					if (++stage == kStages) {
-						stage = 0;
-						phase ^= 1;
+			uint32_t stage = 0, phase = 0, qw = 0;
+			for (;;) {
+				const uint32_t chunk = atomicAdd(P.chunk_counter, 1u);
+				const bool done = chunk >= n_chunks;
+				// announce the chunk (or the end) before its first tile can complete
+				mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+				chunk_q[qw % kQueue] = done ? 0xFFFFFFFFu : chunk;
+				qw++;
+				if (done) {
+					mbar_arrive(bar_full + 8 * stage); // wake the consumers with no data
+					break;
+				}
+				const uint32_t first = chunk * kChunkItems, last = min(first + kChunkItems, P.items);
+				for (uint32_t item = first; item < last; item++) {
+					const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
+					const int x = (int)(strip * kStripPx);
+					for (uint32_t t = 0; t < tiles; t++) {
+						if (!(item == first && t == 0))
+							mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+						const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
+						mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
+						if (L::kLoadRgb)
+							tma_load_3d(dst, &map_rgb, bar_full + 8 * stage, x, (int)(t * kTileRows),
+								    (int)frame);
+						if (L::kLoadYuv)
+							tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), &map_yuv,
+								    bar_full + 8 * stage, x, (int)(t * kTileRows), (int)frame);
+						if (++stage == kStages) {
+							stage = 0;
+							phase ^= 1;
+						}
 					}
 				}
 			}
@@ -351,66 +597,48 @@ __global__ void __launch_bounds__(kConsumerThreads + (USE_TMA ? 32 : 0), 1)
 	}
 
 	// ================= consumers =================
-	const uint32_t vs_base = smem_base + L::kVsOff;
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
-	uint32_t stage = 0, phase = 0;
+	uint32_t magic; // 0x4B000000 kept in a register so PRMT can take the selector as its immediate
+	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
+			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	const Coef coef = P.coef;
+	uint32_t stage = 0, phase = 0, qr = 0;
 	uint32_t cur_frame = 0xFFFFFFFFu;
 
-	auto flush_vscope = [&](uint32_t frame) {
-		// every consumer thread: move its slice of the u16 pairs to the frame's u32 accumulators
-		consumer_bar();
-		uint32_t *acc = P.vscope_acc + (size_t)frame * P.vscope_stride;
-		for (int i = tid; i < kVsWords / 4; i += kConsumerThreads) {
-			uint4 w = reinterpret_cast<uint4 *>(vs)[i];
-			if ((w.x | w.y | w.z | w.w) != 0u) {
-				const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					if (ww[j] & 0xFFFFu)
-						atomicAdd(acc + (i * 4 + j) * 2, ww[j] & 0xFFFFu);
-					if (ww[j] >> 16)
-						atomicAdd(acc + (i * 4 + j) * 2 + 1, ww[j] >> 16);
-				}
-				reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
-			}
-		}
-		consumer_bar();
-	};
+	for (;;) {
+		// the chunk id becomes readable once the chunk's first tile (or the end marker) lands
+		mbar_wait(bar_full + 8 * stage, phase);
+		const uint32_t chunk = chunk_q[qr % kQueue];
+		qr++;
+		if (chunk == 0xFFFFFFFFu)
+			break;
+		const uint32_t first = chunk * kChunkItems, last = min(first + kChunkItems, P.items);
+		for (uint32_t item = first; item < last; item++) {
+			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
+			if (VSCOPE && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
+				flush_vscope<NW>(P, vs, cur_frame, tid);
+			cur_frame = frame;
+			const uint32_t x = strip * kStripPx + lane;
+			const bool lane_ok = x < P.width;
+			const bool strip_full = strip * kStripPx + kStripPx <= P.width;
 
-	for (uint32_t item = first; item < last; item++) {
-		const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
-		if (VSCOPE && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
-			flush_vscope(cur_frame);
-		cur_frame = frame;
-		const uint32_t x = strip * kStripPx + lane;
-		const bool lane_ok = x < P.width;
-		const uint8_t *rgb_px = nullptr, *yuv_px = nullptr;
-		if (!USE_TMA) {
-			rgb_px = P.rgb + (size_t)frame * P.frame_stride + (size_t)(lane_ok ? x : 0) * 4;
-			yuv_px = P.yuv + (size_t)frame * P.frame_stride + (size_t)(lane_ok ? x : 0) * 4;
-		}
-
-		for (uint32_t t = 0; t < tiles; t++) {
-			const uint32_t y0 = t * kTileRows + warp * kRowsPerWarp;
-			uint32_t p[kRowsPerWarp], q[kRowsPerWarp];
-			bool ok[kRowsPerWarp];
+			for (uint32_t t = 0; t < tiles; t++) {
+				const uint32_t y0 = t * kTileRows + warp * RPW;
+				// `full` is uniform over the CTA: every pixel of the 64x32 tile lies inside the frame
+				const bool full = strip_full && (t * kTileRows + kTileRows <= P.height);
+				uint32_t p[RPW], q[RPW];
+				bool ok[RPW];
+				if (!(item == first && t == 0))
+					mbar_wait(bar_full + 8 * stage, phase);
+				const uint32_t *tile =
+					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes);
 #pragma unroll
-			for (int k = 0; k < kRowsPerWarp; k++) {
-				ok[k] = lane_ok && (y0 + k < P.height);
-				p[k] = 0;
-				q[k] = 0;
-			}
-			if (USE_TMA) {
-				mbar_wait(bar_full + 8 * stage, phase);
-				const uint32_t *tile = reinterpret_cast<const uint32_t *>(
-					smem + L::kStageOff + stage * L::kStageBytes);
-#pragma unroll
-				for (int k = 0; k < kRowsPerWarp; k++) {
-					const int o = (warp * kRowsPerWarp + k) * kStripPx + lane;
-					if (L::kLoadRgb)
-						p[k] = tile[o];
-					if (L::kLoadYuv)
-						q[k] = tile[o + (L::kLoadRgb ? kTileBytes / 4 : 0)];
+				for (int k = 0; k < RPW; k++) {
+					const int o = (warp * RPW + k) * kStripPx + lane;
+					ok[k] = full || (lane_ok && (y0 + k < P.height));
+					p[k] = L::kLoadRgb ? tile[o] : 0u;
+					q[k] = L::kLoadYuv ? tile[o + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
 				}
 				__syncwarp();
 				if (lane == 0)
@@ -419,104 +647,89 @@ __global__ void __launch_bounds__(kConsumerThreads + (USE_TMA ? 32 : 0), 1)
 					stage = 0;
 					phase ^= 1;
 				}
-			} else {
-#pragma unroll
-				for (int k = 0; k < kRowsPerWarp; k++) {
-					if (ok[k]) {
-						if (L::kLoadRgb)
-							p[k] = ld_nc_u32(rgb_px + (size_t)(y0 + k) * P.linesize);
-						if (L::kLoadYuv)
-							q[k] = ld_nc_u32(yuv_px + (size_t)(y0 + k) * P.linesize);
-					}
-				}
+				if (full && P.bins_mask == 7u)
+					process_tile<SRC, VSCOPE, SURFACE, true, RPW>(tc, coef, p, q, ok);
+				else
+					process_tile<SRC, VSCOPE, SURFACE, false, RPW>(tc, coef, p, q, ok);
 			}
-
-			// ---- colour transform in registers (fused mode) ----
-			if (!SURFACE && (VSCOPE || SRC == SRC_YUV)) {
-#pragma unroll
-				for (int k = 0; k < kRowsPerWarp; k += 2)
-					rgb_to_yuv_pair<SRC == SRC_YUV>(p[k], p[k + 1], P.coef, q[k], q[k + 1]);
-			}
-
-			// ---- waveform / histogram column bins ----
-			if (SRC != SRC_NONE) {
-#pragma unroll
-				for (int k = 0; k < kRowsPerWarp; k++)
-					bins_add(SRC == SRC_RGB ? p[k] : q[k], wave_lane_addr, ok[k], P.bins_mask);
-			}
-
-			// ---- vectorscope ----
-			if (VSCOPE) {
-				uint32_t idx[kRowsPerWarp];
-#pragma unroll
-				for (int k = 0; k < kRowsPerWarp; k++)
-					idx[k] = vs_index(q[k]);
-				bool same = ok[0];
-#pragma unroll
-				for (int k = 1; k < kRowsPerWarp; k++)
-					same = same && ok[k] && (idx[k] == idx[0]);
-				// (the shuffle must be executed by every lane: no short-circuit around it)
-				const uint32_t idx_lane0 = __shfl_sync(0xFFFFFFFFu, idx[0], 0);
-				same = same && (idx[0] == idx_lane0);
-				if (__all_sync(0xFFFFFFFFu, same)) {
-					// flat block: the whole 4x32 block hits one bin -> one atomic
-					if (lane == 0)
-						vs_add(vs_base, idx[0], 32u * kRowsPerWarp);
-				} else {
-#pragma unroll
-					for (int k = 0; k < kRowsPerWarp; k++)
-						if (ok[k])
-							vs_add(vs_base, idx[k], 1u);
-				}
-			}
-		}
-
-		// ---- end of strip: emit this strip's waveform columns + histogram share ----
-		if (SRC != SRC_NONE) {
-			consumer_bar();
-			uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
-			const uint32_t xo = P.x_offset + x;
-			for (int v = warp; v < 256; v += kConsumerWarps) {
-				const uint32_t w0 = wave0[v * 32 + lane];
-				const uint32_t w1 = wave0[kWaveWords + v * 32 + lane];
-				wave0[v * 32 + lane] = 0;
-				wave0[kWaveWords + v * 32 + lane] = 0;
-				const uint32_t cb = w0 & 0xFFFFu, cg = w0 >> 16, cr = w1 & 0xFFFFu;
-				if (P.hist_mask) {
-					const uint32_t sb = __reduce_add_sync(0xFFFFFFFFu, cb);
-					const uint32_t sg = __reduce_add_sync(0xFFFFFFFFu, cg);
-					const uint32_t sr = __reduce_add_sync(0xFFFFFFFFu, cr);
-					if (lane == 0) {
-						if ((P.hist_mask & 4u) && sr)
-							atomicAdd(hist + v * 4 + 0, sr);
-						if ((P.hist_mask & 2u) && sg)
-							atomicAdd(hist + v * 4 + 1, sg);
-						if ((P.hist_mask & 1u) && sb)
-							atomicAdd(hist + v * 4 + 2, sb);
-					}
-				}
-				if (P.wave_mask && lane_ok) {
-					const uint32_t mb = (P.wave_mask & 1u) ? cb : 0u;
-					const uint32_t mg = (P.wave_mask & 2u) ? cg : 0u;
-					const uint32_t mr = (P.wave_mask & 4u) ? cr : 0u;
-					const size_t o = (size_t)(255 - v) * P.out_width + xo;
-					if (P.partial) {
-						if (mb | mg)
-							atomicAdd(P.wave_pairs + o * 2, mb | (mg << 16));
-						if (mr)
-							atomicAdd(P.wave_pairs + o * 2 + 1, mr);
-					} else {
-						uint32_t *dst = reinterpret_cast<uint32_t *>(
-							P.wave + (size_t)frame * P.wave_stride);
-						dst[o] = min(mb, 255u) | (min(mg, 255u) << 8) | (min(mr, 255u) << 16);
-					}
-				}
-			}
-			consumer_bar();
+			if (SRC != SRC_NONE)
+				emit_strip<NW>(P, wave0, frame, x, lane_ok, warp, lane);
 		}
 	}
 	if (VSCOPE && cur_frame != 0xFFFFFFFFu)
-		flush_vscope(cur_frame);
+		flush_vscope<NW>(P, vs, cur_frame, tid);
+}
+
+// ---------------------------------------------------------------------------
+// strip kernel, plain-load fallback for planes TMA cannot describe (base or pitch not a
+// multiple of 16 bytes, e.g. an ROI crop at an odd column).  Same accumulation code; each
+// thread simply loads its own pixels (128 B per warp-row) right before using them.
+// ---------------------------------------------------------------------------
+template <int SRC, bool VSCOPE, bool SURFACE>
+__global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(const __grid_constant__ StripParams P)
+{
+	using L = SmemLayout<SRC, VSCOPE, SURFACE, false>;
+	constexpr int NW = kLdgWarps, RPW = kLdgRows;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
+	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
+	const uint32_t smem_base = smem_u32(smem);
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5, lane = tid & 31;
+
+	zero_bins<NW>(vs, wave0, VSCOPE, SRC != SRC_NONE, tid);
+	__syncthreads();
+
+	const uint32_t first = blockIdx.x * P.items_per_cta;
+	const uint32_t last = min(first + P.items_per_cta, P.items);
+	const uint32_t groups = (P.height + RPW - 1) / RPW;
+
+	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
+	uint32_t magic;
+	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
+			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	const Coef coef = P.coef;
+	uint32_t cur_frame = 0xFFFFFFFFu;
+
+	for (uint32_t item = first; item < last; item++) {
+		const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
+		if (VSCOPE && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
+			flush_vscope<NW>(P, vs, cur_frame, tid);
+		cur_frame = frame;
+		const uint32_t x = strip * kStripPx + lane;
+		const bool lane_ok = x < P.width;
+		const bool strip_full = strip * kStripPx + kStripPx <= P.width;
+		const size_t col = (size_t)frame * P.frame_stride + (size_t)(lane_ok ? x : 0) * 4;
+
+		for (uint32_t g = warp; g < groups; g += NW) {
+			const uint32_t y0 = g * RPW;
+			const bool full = strip_full && (y0 + RPW <= P.height);
+			uint32_t p[RPW], q[RPW];
+			bool ok[RPW];
+#pragma unroll
+			for (int k = 0; k < RPW; k++) {
+				ok[k] = full || (lane_ok && (y0 + k < P.height));
+				p[k] = 0;
+				q[k] = 0;
+				if (ok[k]) {
+					const size_t o = col + (size_t)(y0 + k) * P.linesize;
+					if (L::kLoadRgb)
+						p[k] = ld_nc_u32(P.rgb + o);
+					if (L::kLoadYuv)
+						q[k] = ld_nc_u32(P.yuv + o);
+				}
+			}
+			if (full && P.bins_mask == 7u)
+				process_tile<SRC, VSCOPE, SURFACE, true, RPW>(tc, coef, p, q, ok);
+			else
+				process_tile<SRC, VSCOPE, SURFACE, false, RPW>(tc, coef, p, q, ok);
+		}
+		if (SRC != SRC_NONE)
+			emit_strip<NW>(P, wave0, frame, x, lane_ok, warp, lane);
+	}
+	if (VSCOPE && cur_frame != 0xFFFFFFFFu)
+		flush_vscope<NW>(P, vs, cur_frame, tid);
 }
 
 // ---------------------------------------------------------------------------
@@ -611,11 +824,14 @@ __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out
 {
 	const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 2;
 	// index r<<16|g<<8|b is already the little-endian BGRA word b | g<<8 | r<<16
-	const uint32_t pa = i | 0xFF000000u, pb = (i + 1) | 0xFF000000u;
-	uint32_t qa, qb;
-	rgb_to_yuv_pair<true>(pa, pb, coef, qa, qb);
-	out[i] = qa & 0xFFFFFFu;
-	out[i + 1] = qb & 0xFFFFFFu;
+	uint32_t magic;
+	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+	const uint32_t ca[3] = {carrier<0>(i, magic), carrier<1>(i, magic), carrier<2>(i, magic)};
+	const uint32_t cb[3] = {carrier<0>(i + 1, magic), carrier<1>(i + 1, magic), carrier<2>(i + 1, magic)};
+	uint32_t ya[3], yb[3];
+	rgb_to_yuv_pair<true>(ca, cb, coef, ya, yb);
+	out[i] = (ya[0] & 0xFFu) | ((ya[1] & 0xFFu) << 8) | ((ya[2] & 0xFFu) << 16);
+	out[i + 1] = (yb[0] & 0xFFu) | ((yb[1] & 0xFFu) << 8) | ((yb[2] & 0xFFu) << 16);
 }
 
 } // namespace scope
