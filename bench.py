@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--colorspace", type=int, default=2)
     ap.add_argument("--e2e-frames", type=int, default=16, help="frames per step on the host-buffer path")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = one frame per host thread (bounded)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "roi-tiled-8k", "stream-vscope-4k"],
+                    help="batch = the headline (BASELINE config 5 / metric); roi-tiled-8k = config 4; "
+                         "stream-vscope-4k = config 3")
+    ap.add_argument("--bands", default="rows", choices=["rows", "cols"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -396,10 +400,133 @@ def run_e2e(args, eng, st, batch, dev, world, rank):
             "path": "scope_submit_host/scope_wait_host, 3-slot ring, pinned host frames, wall clock max over ranks"}
 
 
+def run_roi_tiled(args):
+    """BASELINE config 4: ONE 7680x4320 frame, waveform of luma (components 0x20), split into row
+    bands (or column bands) over the ranks; partial u16-pair bins all-reduced with NCCL, then
+    saturated.  A step = one frame."""
+    import torch
+    import torch.distributed as dist
+
+    import obs_color_monitor_b200 as pkg
+    from obs_color_monitor_b200 import frames_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = 7680, 4320
+    eng = pkg.ScopeEngine(local_rank)
+    st = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=pkg.COMP_Y, colorspace=args.colorspace)
+    tiled = pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
+    a, b = tiled.my_band
+    # 4 different frames so that successive steps do not hit L2 (8K frame = 133 MB > L2 anyway)
+    if args.bands == "rows":
+        bands = [frames_torch.mixed_batch(1, W, b - a, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
+    else:
+        full = [frames_torch.mixed_batch(1, W, H, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
+        bands = [torch.as_strided(f.reshape(-1)[a * 4:], (H, (W - a) * 4), (W * 4, 1)) for f in full]
+
+    def step(i):
+        tiled.reset()
+        tiled.accumulate(bands[i % 4], width=(b - a) if args.bands == "cols" else None)
+        return tiled.reduce_and_finalize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        out = step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count
+    ev0.record()
+    for i in range(args.steps):
+        out = step(i)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    assert int(out["wave"][0, :, :, 1].to(torch.int64).sum()) > 0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "frames/sec ROI-tiled waveform (luma) @7680x4320 BGRA", "value": args.steps / (ms * 1e-3),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 (fp32 colour transform)", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: one 7680x4320 frame, luma waveform, {args.bands} bands over "
+                                   f"{world} GPU(s), all-reduce of 256x7680 u16x2 pairs ({256 * 7680 * 8 / 1e6:.1f} MB) "
+                                   f"then saturate", "bands": args.bands},
+            "gpu_launches": eng.launch_count - l0,
+            "achieved_read_GBps": args.steps * W * H * 4 / (ms * 1e-3) / 1e9}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def run_stream_vscope(args):
+    """BASELINE config 3: a 3840x2160 stream through the 3-slot host ring, vectorscope only,
+    with the intensity-applied display image (intensity 25).  Reports sustained fps and the
+    latency of a single synchronous frame."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import obs_color_monitor_b200 as pkg
+    from obs_color_monitor_b200 import frames_torch
+
+    torch.cuda.set_device(0)
+    eng = pkg.ScopeEngine(0)
+    W, H, nf = 3840, 2160, 12
+    st = pkg.ScopeSettings(scopes=pkg.SCOPE_VSCOPE, vscope_intensity=25, colorspace=args.colorspace)
+    lib = eng.lib
+    ptr = lib.scope_host_alloc(nf * W * H * 4)
+    host = np.ctypeslib.as_array((C.c_uint8 * (nf * W * H * 4)).from_address(ptr)).reshape(nf, H, W, 4)
+    host[:] = frames_torch.mixed_batch(nf, W, H, torch.device("cuda", 0)).cpu().numpy()
+    lat = []
+    for i in range(6):
+        t0 = time.perf_counter()
+        res = eng.accumulate_host(host[i % nf], settings=st)
+        lat.append(time.perf_counter() - t0)
+    n = 60 * max(args.steps, 1)
+    t0 = time.perf_counter()
+    for i in range(n):
+        sl = i % 3
+        if i >= 3:
+            eng.wait_host(sl)
+        assert eng.submit_host(sl, host[i % nf], settings=st)
+    for i in range(n - 3, n):
+        res = eng.wait_host(i % 3)
+    dt = time.perf_counter() - t0
+    assert res["vscope"].max() > 0 and res["vscope_display"].max() == 255
+    lib.scope_host_free(ptr)
+    print(json.dumps({
+        "metric": "frames/sec vectorscope+intensity stream @3840x2160 BGRA (host ring)", "value": n / dt,
+        "unit": "frames/s", "n_gpus": 1, "steps": n, "warmup": 6, "ms_per_step": 1e3 * dt / n,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (fp32 colour transform)",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config 3: 3840x2160 stream, 3-slot ring (CM_SURFACE_QUEUE_SIZE), vectorscope "
+                               "256x256 + intensity 25 display image, pinned host frames in, host results out",
+                   "sync_frame_latency_ms": 1e3 * min(lat), "realtime_60fps_headroom": (n / dt) / 60.0},
+        "gpu_launches": eng.launch_count}), flush=True)
+    eng.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "roi-tiled-8k":
+        run_roi_tiled(args)
+    elif args.workload == "stream-vscope-4k":
+        run_stream_vscope(args)
     else:
         run_b200_arm(args)
 

@@ -8,7 +8,7 @@ The directory name carries a hyphen (it is the name the task fixes); import it a
 Nothing in this package imports ``oracle/``: the CUDA library is the only implementation,
 and loading fails loudly when it has not been built.
 """
-from . import _ffi, frames  # noqa: F401
+from . import _ffi, frames, sharding  # noqa: F401
 from ._ffi import (COMP_RGB, COMP_UV, COMP_Y, COMP_YUV, MODE_FUSED, MODE_SURFACE, SCOPE_ALL, SCOPE_HIST,  # noqa: F401
                    SCOPE_VSCOPE, SCOPE_WAVE, ScopeError)
 from .scopes import ScopeEngine, ScopeSettings  # noqa: F401

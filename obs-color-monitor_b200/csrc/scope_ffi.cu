@@ -288,8 +288,11 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	if (grid > P.items)
 		grid = P.items;
 	if (use_tma) {
-		// chunks of kChunkItems strips are claimed at run time from a zeroed counter
-		const uint32_t n_chunks = (P.items + kChunkItems - 1) / kChunkItems;
+		// chunks of strips are claimed at run time from a zeroed counter: big enough to keep
+		// vectorscope flushes rare, small enough that every CTA gets >= ~6 of them
+		uint32_t ch = P.items / (grid * 6u);
+		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
+		const uint32_t n_chunks = (P.items + P.chunk_items - 1) / P.chunk_items;
 		if (grid > n_chunks)
 			grid = n_chunks;
 		if (!ctx->d_counters)

@@ -28,7 +28,7 @@ constexpr int kTileRows = 64;         // rows per TMA tile
 constexpr int kTmaWarps = 16;         // consumer warps of the TMA kernel (4 rows of each tile per warp)
 constexpr int kMaxStages = 4;         // depth of the tile ring (what the bins leave room for)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
-constexpr int kChunkItems = 10;       // strips per dynamically claimed chunk
+constexpr int kMaxChunkItems = 10;    // upper bound of strips per dynamically claimed chunk
 constexpr int kQueue = 4;             // chunk-id mailbox entries (producer is < kQueue chunks ahead)
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
@@ -48,7 +48,8 @@ struct StripParams {
 	uint32_t linesize, width, height, n_frames;
 	uint32_t strips;          // per frame
 	uint32_t items;           // n_frames * strips
-	uint32_t items_per_cta;
+	uint32_t items_per_cta;   // plain-load kernel: static share of each CTA
+	uint32_t chunk_items;     // TMA kernel: strips per dynamically claimed chunk
 	uint32_t bins_mask;       // channels accumulated into the column bins: bit0 B|U, bit1 G|Y, bit2 R|V
 	uint32_t hist_mask;       // channels the histogram output wants
 	uint32_t wave_mask;       // channels the waveform output wants
@@ -514,7 +515,7 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 }
 
 // ---------------------------------------------------------------------------
-// strip kernel, TMA loader.  A producer warp (one elected lane) walks CHUNKS of kChunkItems
+// strip kernel, TMA loader.  A producer warp (one elected lane) walks CHUNKS of P.chunk_items
 // consecutive strips, claimed from a global counter so that fast and slow frame content
 // balances across CTAs, and fills a kStages-deep shared-memory ring of 64-row x 128-byte
 // tiles with cp.async.bulk.tensor.  16 consumer warps take 4 rows of every tile each.
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 	__syncthreads();
 
 	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
-	const uint32_t n_chunks = (P.items + kChunkItems - 1) / kChunkItems;
+	const uint32_t n_chunks = (P.items + P.chunk_items - 1) / P.chunk_items;
 
 	if (is_producer) {
 		// ================= TMA producer (one elected lane) =================
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 					mbar_arrive(bar_full + 8 * stage); // wake the consumers with no data
 					break;
 				}
-				const uint32_t first = chunk * kChunkItems, last = min(first + kChunkItems, P.items);
+				const uint32_t first = chunk * P.chunk_items, last = min(first + P.chunk_items, P.items);
 				for (uint32_t item = first; item < last; item++) {
 					const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
 					const int x = (int)(strip * kStripPx);
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 		qr++;
 		if (chunk == 0xFFFFFFFFu)
 			break;
-		const uint32_t first = chunk * kChunkItems, last = min(first + kChunkItems, P.items);
+		const uint32_t first = chunk * P.chunk_items, last = min(first + P.chunk_items, P.items);
 		for (uint32_t item = first; item < last; item++) {
 			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
 			if (VSCOPE && frame != cur_frame && cur_frame != 0xFFFFFFFFu)

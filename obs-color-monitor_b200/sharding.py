@@ -1,0 +1,121 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+Two ways the path shards; the reference has neither (it is single threaded):
+
+* frame sharding  — frames are independent (every frame re-zeroes its bins:
+  histogram.c:363-365, waveform.c:225-226, vectorscope.c:219-220), so rank r takes a
+  contiguous share of the batch and NO data-path collective is needed; `gather_results`
+  is only for callers that want everything on one rank.
+* tile sharding of ONE frame — row bands (or column bands) per rank; the partial bins are
+  additive, so the ranks all-reduce them (NCCL sum over int32 lanes) and then apply the
+  saturation the reference applies per increment: min(sum of partials, 255).
+  With column bands the waveform needs no reduction at all (disjoint columns).
+
+Nothing here touches the oracle; the accumulation itself is `ScopeEngine.accumulate_partial`.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+STRIP = 32  # the kernels work in strips of 32 columns; column bands are aligned to it
+
+
+def frame_shard(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous share of `n_frames` for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def row_bands(height: int, world: int) -> List[Tuple[int, int]]:
+    """[y0, y1) per rank; bands differ by at most one row."""
+    return [(r.start, r.stop) for r in (frame_shard(height, k, world) for k in range(world))]
+
+
+def col_bands(width: int, world: int) -> List[Tuple[int, int]]:
+    """[x0, x1) per rank, boundaries on multiples of 32 columns (whole strips per rank)."""
+    strips = (width + STRIP - 1) // STRIP
+    out = []
+    for k in range(world):
+        s = frame_shard(strips, k, world)
+        out.append((min(s.start * STRIP, width), min(s.stop * STRIP, width)))
+    return out
+
+
+def allreduce_partials(partial: Dict[str, "torch.Tensor"], keys=("hist", "wave_pairs", "vscope"), group=None):
+    """In-place sum of the partial accumulators over all ranks.  The tensors are int32 views of
+    u32 counts / u16x2 pairs: every lane stays below 2^31 (hist: <= W*H, pairs: each u16 half
+    <= rows of the whole frame <= 65535, vscope: <= W*H), so integer addition is exact and carries
+    never cross a u16 half."""
+    import torch.distributed as dist
+
+    works = [dist.all_reduce(partial[k], op=dist.ReduceOp.SUM, group=group, async_op=True) for k in keys
+             if k in partial]
+    for w in works:
+        w.wait()
+    return partial
+
+
+def gather_results(out: Dict[str, "torch.Tensor"], dst: int = 0, group=None) -> Optional[Dict[str, list]]:
+    """Optional: collect every rank's per-frame outputs on `dst` (frame-sharded jobs)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    res = {}
+    for k, t in out.items():
+        bufs = [torch.empty_like(t) for _ in range(world)] if dist.get_rank(group) == dst else None
+        dist.gather(t, bufs, dst=dst, group=group)
+        if bufs is not None:
+            res[k] = bufs
+    return res if dist.get_rank(group) == dst else None
+
+
+class TiledFrame:
+    """One frame split across ranks.  Each rank calls `accumulate(band_tensor)` with ITS band
+    (device tensor) and then `reduce_and_finalize()`; every rank ends with the full result."""
+
+    def __init__(self, engine, full_width: int, full_height: int, settings, mode: str = "rows", group=None):
+        import torch.distributed as dist
+
+        assert mode in ("rows", "cols")
+        self.engine, self.settings, self.mode, self.group = engine, settings, mode, group
+        self.width, self.height = full_width, full_height
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bands = row_bands(full_height, self.world) if mode == "rows" else col_bands(full_width, self.world)
+        self.partial = engine.alloc_partial(full_width)
+
+    @property
+    def my_band(self) -> Tuple[int, int]:
+        return self.bands[self.rank]
+
+    def reset(self):
+        for t in self.partial.values():
+            t.zero_()
+
+    def accumulate(self, band, width: Optional[int] = None):
+        """band: this rank's rows (rows mode: (h_band, W, 4)) or columns (cols mode: a
+        (H, linesize) byte view starting at column x0, with `width` = x1 - x0)."""
+        a, b = self.my_band
+        if self.mode == "rows":
+            self.engine.accumulate_partial(band, self.partial, x_offset=0, full_width=self.width,
+                                           settings=self.settings, width=width)
+        else:
+            self.engine.accumulate_partial(band, self.partial, x_offset=a, full_width=self.width,
+                                           settings=self.settings, width=(b - a) if width is None else width)
+
+    def reduce_and_finalize(self):
+        from ._ffi import SCOPE_HIST, SCOPE_VSCOPE, SCOPE_WAVE
+
+        if self.world > 1:
+            keys = []
+            if self.settings.scopes & SCOPE_HIST:
+                keys.append("hist")
+            if self.settings.scopes & SCOPE_WAVE:
+                keys.append("wave_pairs")       # cols mode: disjoint columns, the sum just merges them
+            if self.settings.scopes & SCOPE_VSCOPE:
+                keys.append("vscope")
+            allreduce_partials(self.partial, keys, self.group)
+        return self.engine.finalize_partial(self.partial, full_width=self.width, full_height=self.height,
+                                            settings=self.settings)
