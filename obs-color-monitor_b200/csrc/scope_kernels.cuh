@@ -108,7 +108,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t val)
 {
 	uint32_t old;
-	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(val) : "memory");
+	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(val));
 	return old;
 }
 __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
@@ -250,7 +250,7 @@ struct SmemLayout {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void red_shared(uint32_t addr, uint32_t val)
 {
-	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val));
 }
 
 // Waveform / histogram column bins: plane0[level][lane] = (count B|U : lo16, count G|Y : hi16),
@@ -283,10 +283,11 @@ struct VsAdd {
 __device__ __forceinline__ VsAdd vs_add(uint32_t vs_base, uint32_t idx, uint32_t k)
 {
 	VsAdd r;
+	const uint32_t h = idx >> 15;            // 0: lower half (V < 128), 1: upper half
 	r.addr = (idx & 0x7FFFu) * 4u + vs_base;
-	r.add = (idx >> 15) * (k * 0xFFFFu) + k; // k << 16 for the upper half, k for the lower
+	r.add = h * (k * 0xFFFFu) + k;           // k << 16 for the upper half, k for the lower
 	const uint32_t old = atom_shared_add(r.addr, r.add);
-	r.sat = old & ((idx >> 15) * 0x7FFF8000u + 0x8000u);
+	r.sat = old & (h * 0x7FFF8000u + 0x8000u);
 	return r;
 }
 __device__ __forceinline__ void vs_undo(const VsAdd &a)
@@ -515,6 +516,116 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 }
 
 // ---------------------------------------------------------------------------
+// Two-phase form of the interior-tile body (tile completely inside the frame, all three
+// channels on): prepare_tile = carriers, colour transform, indices and the two warp votes;
+// commit_tile = the shared-memory atomics.  The TMA kernel runs commit(tile t) and
+// prepare(tile t+1) back to back so that a warp overlaps the LSU work of one tile with the
+// FP32 work of the next instead of alternating between the two pipes.
+// ---------------------------------------------------------------------------
+template <int N>
+struct Prep {
+	uint32_t cs[N][3]; // carriers of the three bytes the column bins look at
+	uint32_t a[N];     // the word whose alpha decides whether the pixel counts
+	uint32_t idx[N];   // vectorscope bin, U | V << 8
+	bool all_counted;  // warp-uniform: every pixel of the warp's N x 32 block counts
+	bool flat;         // warp-uniform: the whole block hits one vectorscope bin
+};
+
+template <int SRC, bool VSCOPE, bool SURFACE, int N>
+__device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef, const uint32_t (&p)[N],
+					     const uint32_t (&q)[N], Prep<N> &o)
+{
+	constexpr bool kTransform = !SURFACE && (VSCOPE || SRC == SRC_YUV);
+	uint32_t crgb[N][3], cyuv[N][3];
+	if (SRC == SRC_RGB || kTransform) {
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			crgb[k][0] = carrier<0>(p[k], c.magic);
+			crgb[k][1] = carrier<1>(p[k], c.magic);
+			crgb[k][2] = carrier<2>(p[k], c.magic);
+		}
+	}
+	if (kTransform) {
+#pragma unroll
+		for (int k = 0; k < N; k += 2)
+			rgb_to_yuv_pair<SRC == SRC_YUV>(crgb[k], crgb[k + 1], coef, cyuv[k], cyuv[k + 1]);
+	} else if (SURFACE && SRC == SRC_YUV) {
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			cyuv[k][0] = carrier<0>(q[k], c.magic);
+			cyuv[k][1] = carrier<1>(q[k], c.magic);
+			cyuv[k][2] = carrier<2>(q[k], c.magic);
+		}
+	}
+	o.all_counted = true;
+	if (SRC != SRC_NONE) {
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			o.cs[k][0] = SRC == SRC_RGB ? crgb[k][0] : cyuv[k][0];
+			o.cs[k][1] = SRC == SRC_RGB ? crgb[k][1] : cyuv[k][1];
+			o.cs[k][2] = SRC == SRC_RGB ? crgb[k][2] : cyuv[k][2];
+		}
+		if (SRC == SRC_RGB || SURFACE) {
+			uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				o.a[k] = SRC == SRC_RGB ? p[k] : q[k];
+				m = min(m, o.a[k]);
+			}
+			o.all_counted = __all_sync(0xFFFFFFFFu, m > 0x00FFFFFFu);
+		}
+	}
+	o.flat = false;
+	if (VSCOPE) {
+#pragma unroll
+		for (int k = 0; k < N; k++)
+			o.idx[k] = SURFACE ? __byte_perm(q[k], 0u, 0x4420) : __byte_perm(cyuv[k][0], cyuv[k][2], 0x1140);
+		bool same = true;
+#pragma unroll
+		for (int k = 1; k < N; k++)
+			same = same && (o.idx[k] == o.idx[0]);
+		const uint32_t idx_lane0 = __shfl_sync(0xFFFFFFFFu, o.idx[0], 0);
+		o.flat = __all_sync(0xFFFFFFFFu, same && (o.idx[0] == idx_lane0));
+	}
+}
+
+template <int SRC, bool VSCOPE, bool SURFACE, int N>
+__device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
+{
+	if (SRC != SRC_NONE) {
+		if (o.all_counted) {
+#pragma unroll
+			for (int k = 0; k < N; k++)
+				bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, 1u);
+		} else {
+#pragma unroll
+			for (int k = 0; k < N; k++)
+				bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1,
+							   o.a[k] > 0x00FFFFFFu ? 1u : 0u);
+		}
+	}
+	if (VSCOPE) {
+		if (o.flat) {
+			if (c.lane == 0)
+				vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
+		} else {
+			VsAdd a[N];
+			uint32_t any = 0;
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				a[k] = vs_add(c.vs_base, o.idx[k], 1u);
+				any |= a[k].sat;
+			}
+			if (any) {
+#pragma unroll
+				for (int k = 0; k < N; k++)
+					vs_undo(a[k]);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
 // strip kernel, TMA loader.  A producer warp (one elected lane) walks CHUNKS of P.chunk_items
 // consecutive strips, claimed from a global counter so that fast and slow frame content
 // balances across CTAs, and fills a kStages-deep shared-memory ring of 64-row x 128-byte
@@ -604,6 +715,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
 			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
+	const bool fast_cfg = P.bins_mask == 7u;
+	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
+	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
 	uint32_t stage = 0, phase = 0, qr = 0;
 	uint32_t cur_frame = 0xFFFFFFFFu;
 
@@ -624,34 +738,84 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 			const bool lane_ok = x < P.width;
 			const bool strip_full = strip * kStripPx + kStripPx <= P.width;
 
-			for (uint32_t t = 0; t < tiles; t++) {
-				const uint32_t y0 = t * kTileRows + warp * RPW;
-				// `full` is uniform over the CTA: every pixel of the 64x32 tile lies inside the frame
-				const bool full = strip_full && (t * kTileRows + kTileRows <= P.height);
-				uint32_t p[RPW], q[RPW];
-				bool ok[RPW];
-				if (!(item == first && t == 0))
+			// tiles [0, n_full) lie completely inside the frame (uniform over the CTA)
+			const uint32_t n_full = (strip_full && fast_cfg) ? P.height / kTileRows : 0u;
+			bool skip_wait = item == first; // the chunk announcement already waited for tile 0
+			// fetch = wait for the tile, read this thread's pixels, remember which stage to hand back
+			auto fetch_tile = [&](uint32_t(&p)[RPW], uint32_t(&q)[RPW]) -> uint32_t {
+				if (!skip_wait)
 					mbar_wait(bar_full + 8 * stage, phase);
+				skip_wait = false;
 				const uint32_t *tile =
-					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes);
+					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes) +
+					warp * RPW * kStripPx + lane;
 #pragma unroll
 				for (int k = 0; k < RPW; k++) {
-					const int o = (warp * RPW + k) * kStripPx + lane;
-					ok[k] = full || (lane_ok && (y0 + k < P.height));
-					p[k] = L::kLoadRgb ? tile[o] : 0u;
-					q[k] = L::kLoadYuv ? tile[o + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
+					p[k] = L::kLoadRgb ? tile[k * kStripPx] : 0u;
+					q[k] = L::kLoadYuv ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
 				}
-				__syncwarp();
-				if (lane == 0)
-					mbar_arrive(bar_empty + 8 * stage);
+				const uint32_t bar = bar_empty + 8 * stage;
 				if (++stage == kStages) {
 					stage = 0;
 					phase ^= 1;
 				}
-				if (full && P.bins_mask == 7u)
-					process_tile<SRC, VSCOPE, SURFACE, true, RPW>(tc, coef, p, q, ok);
-				else
-					process_tile<SRC, VSCOPE, SURFACE, false, RPW>(tc, coef, p, q, ok);
+				return bar;
+			};
+			// release = hand the stage back to the producer.  The barrier address is made to
+			// depend on the loaded pixels (`& zero`, an opaque 0) so the arrive cannot be issued
+			// before the LDS results are in registers: under a backlog of serialised atomics the
+			// LSU can otherwise still be holding those reads when the TMA refill lands (seen as
+			// rare wrong-bin pixels on smooth content; profiles/ubench_r01.md, "WAR on the ring").
+			auto release_tile = [&](uint32_t bar, const uint32_t(&p)[RPW], const uint32_t(&q)[RPW]) {
+				uint32_t dep = 0;
+#pragma unroll
+				for (int k = 0; k < RPW; k++)
+					dep |= p[k] | q[k];
+				__syncwarp();
+				if (lane == 0)
+					mbar_arrive(bar + (dep & zero));
+			};
+			uint32_t t = 0;
+			if (n_full > 0) {
+				// software pipeline over the interior tiles: atomics of tile t next to the
+				// arithmetic of tile t+1 (two Prep register sets, ping-pong)
+				uint32_t p[RPW], q[RPW];
+				Prep<RPW> A, B;
+				uint32_t bar = fetch_tile(p, q);
+				release_tile(bar, p, q);
+				prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, A);
+				for (t = 1; t + 1 < n_full; t += 2) {
+					bar = fetch_tile(p, q);
+					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+					release_tile(bar, p, q);
+					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, B);
+					bar = fetch_tile(p, q);
+					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, B);
+					release_tile(bar, p, q);
+					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, A);
+				}
+				if (t < n_full) {
+					bar = fetch_tile(p, q);
+					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+					release_tile(bar, p, q);
+					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, B);
+					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, B);
+				} else {
+					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+				}
+				t = n_full;
+			}
+			for (; t < tiles; t++) {
+				// edge tiles (last rows, last strip) and partial channel masks: generic body
+				uint32_t p[RPW], q[RPW];
+				bool ok[RPW];
+				const uint32_t bar = fetch_tile(p, q);
+				release_tile(bar, p, q);
+				const uint32_t y0 = t * kTileRows + warp * RPW;
+#pragma unroll
+				for (int k = 0; k < RPW; k++)
+					ok[k] = lane_ok && (y0 + k < P.height);
+				process_tile<SRC, VSCOPE, SURFACE, false, RPW>(tc, coef, p, q, ok);
 			}
 			if (SRC != SRC_NONE)
 				emit_strip<NW>(P, wave0, frame, x, lane_ok, warp, lane);
