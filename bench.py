@@ -178,7 +178,7 @@ def run_reference_arm(args):
     sample = (f"{n} {args.content} {args.width}x{args.height} frames per step, the reference's hist RGB + waveform RGB "
               f"+ vectorscope loops, one frame per thread over {threads} threads, YUV plane precomputed")
     line = {
-        "impl": "reference", "metric": "frames/sec fused scopes @3840x2160 BGRA", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "frames_per_step": n, "width": args.width, "height": args.height},
@@ -187,6 +187,10 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(args):
+    return f"frames/sec fused scopes @{args.width}x{args.height} BGRA"
 
 
 def workload_name(args):
@@ -287,7 +291,7 @@ def run_b200_arm(args):
                 "kernel_share_of_step": (k_ms * launches_per_step) / (elapsed_ms / args.steps)}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        roofline["traffic"] = tr["dram_bytes_per_frame"] * n / launches_per_step
         roofline["traffic_note"] = tr.get("note")
     except Exception:
         pass
@@ -310,7 +314,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         line = {
-            "metric": "frames/sec fused scopes @3840x2160 BGRA", "value": value, "unit": "frames/s",
+            "metric": metric_name(args), "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (fp32 colour transform)",
             "data": "synthetic",
