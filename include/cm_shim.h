@@ -99,6 +99,10 @@ struct b200_roi_source {
 	/* scratch for the fused result */
 	uint8_t *wave_tmp;
 	uint32_t wave_tmp_width;
+	/* frame interleave (roi.c:96-100,266-277,523-532; doc/dock.md:58-65): with n_interleave = 1
+	 * (the reference's default) staging happens on every other tick */
+	int n_interleave, i_interleave;
+	bool interleave_rendered;
 };
 
 void b200_roi_init(struct b200_roi_source *roi, scope_ctx *ctx, uint32_t mode);
@@ -151,6 +155,13 @@ void b200_cm_tick(struct b200_cm_source *src);
  * frame was already rendered in this tick (common.c:225-227). */
 bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const uint8_t *yuv, uint32_t linesize,
 			   uint32_t width, uint32_t height);
+/* ROI pacing around the capture core: call b200_roi_tick then b200_roi_target_render once per frame.
+ * roi_tick (roi.c:523-532) only ticks the capture core on the staging phase of the interleave;
+ * roi_target_render (roi.c:266-277) only stages on that phase.  Returns what the reference returns
+ * (true = nothing more to do this frame). */
+void b200_roi_tick(struct b200_roi_source *roi, struct b200_cm_source *cm);
+bool b200_roi_target_render(struct b200_roi_source *roi, struct b200_cm_source *cm, const uint8_t *rgb,
+			    const uint8_t *yuv, uint32_t linesize, uint32_t width, uint32_t height);
 /* test helper: block until the worker has consumed everything queued so far */
 void b200_cm_drain(struct b200_cm_source *src);
 

@@ -479,6 +479,25 @@ bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const
 	return true;
 }
 
+void b200_roi_tick(struct b200_roi_source *roi, struct b200_cm_source *cm)
+{
+	if (roi->interleave_rendered && roi->i_interleave++ >= roi->n_interleave)
+		roi->i_interleave = 0;
+	roi->interleave_rendered = false;
+	if (roi->i_interleave == 0 || roi->n_interleave <= 0)
+		b200_cm_tick(cm);
+}
+
+bool b200_roi_target_render(struct b200_roi_source *roi, struct b200_cm_source *cm, const uint8_t *rgb,
+			    const uint8_t *yuv, uint32_t linesize, uint32_t width, uint32_t height)
+{
+	roi->interleave_rendered = true;
+	if (roi->i_interleave != 0 && roi->n_interleave > 0)
+		return true;
+	b200_cm_render_target(cm, rgb, yuv, linesize, width, height);
+	return roi->n_interleave <= 0;
+}
+
 void b200_cm_drain(struct b200_cm_source *src)
 {
 	pthread_mutex_lock(&src->pipeline_mutex);

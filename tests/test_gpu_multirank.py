@@ -1,0 +1,79 @@
+"""N=2 GPU test (skipped with fewer than 2 GPUs): tile-sharded frame over NCCL == whole frame on
+one GPU, for row bands and column bands; frame-sharded batch gathered on rank 0 == single-GPU batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import obs_color_monitor_b200 as pkg
+    from obs_color_monitor_b200 import frames_torch
+    eng = pkg.ScopeEngine(rank)
+    ok = True
+    w, h = 1000, 700
+    full = frames_torch.mixed_batch(1, w, h, dev, first_index=3, content="natural")[0]   # same seed on every rank
+    whole = eng.accumulate_device(full[None])
+    for mode in ("rows", "cols"):
+        tiled = pkg.sharding.TiledFrame(eng, w, h, pkg.ScopeSettings(), mode=mode)
+        a, b = tiled.my_band
+        if mode == "rows":
+            tiled.accumulate(full[a:b])
+        else:
+            band = torch.as_strided(full.reshape(-1)[a * 4:], (h, (w - a) * 4), (w * 4, 1))
+            tiled.accumulate(band, width=b - a)
+        out = tiled.reduce_and_finalize()
+        torch.cuda.synchronize()
+        for k in ("hist", "wave", "vscope"):
+            ok = ok and bool(torch.equal(out[k][0], whole[k][0]))
+    # frame sharding + optional gather
+    n = 6
+    batch = frames_torch.mixed_batch(n, 640, 360, dev)
+    ref = eng.accumulate_device(batch)
+    mine = pkg.sharding.frame_shard(n, rank, world)
+    part = eng.accumulate_device(batch[mine.start:mine.stop].contiguous())
+    got = pkg.sharding.gather_results({k: part[k] for k in ("hist", "wave", "vscope")}, dst=0)
+    if rank == 0:
+        for k in ("hist", "wave", "vscope"):
+            cat = torch.cat([t.to(dev) for t in got[k]], dim=0)
+            ok = ok and bool(torch.equal(cat, ref[k]))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+    eng.close()
+
+
+def test_two_gpus_tiled_and_sharded():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

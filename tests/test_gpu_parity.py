@@ -195,3 +195,36 @@ def test_partial_tiles_equal_whole_frame(engine, oracle, pkg):
         assert np.array_equal(out["hist"][0].cpu().numpy().view(np.uint32), oracle.histogram_counts(7, f, yuv))
         assert np.array_equal(out["wave"][0].cpu().numpy(), oracle.waveform(7, f, yuv)), bands
         assert np.array_equal(out["vscope"][0].cpu().numpy(), oracle.vectorscope(yuv))
+
+
+def test_error_codes_and_limits(engine, pkg):
+    """bad requests fail with the documented status instead of computing something else"""
+    import torch
+    E = pkg._ffi
+    f = pkg.frames.random(64, 48, seed=1)
+    with pytest.raises(pkg.ScopeError) as e:                      # vectorscope in surface mode needs the YUV plane
+        engine.accumulate_host(f, None, settings=pkg.ScopeSettings(mode=pkg.MODE_SURFACE))
+    assert e.value.code == E.SCOPE_ERR_INVALID
+    with pytest.raises(pkg.ScopeError) as e:                      # linesize < width*4
+        engine.accumulate_host(np.zeros((8, 16), np.uint8), settings=pkg.ScopeSettings(), width=8)
+    assert e.value.code == E.SCOPE_ERR_INVALID
+    tall = torch.zeros((1, 70000, 4, 4), dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.ScopeError) as e:                      # u16 column bins: height <= 65535
+        engine.accumulate_device(tall)
+    assert e.value.code == E.SCOPE_ERR_UNSUPPORTED
+    # the context is still usable afterwards
+    res = engine.accumulate_host(f)
+    assert res["hist"].sum() == 3 * 64 * 48
+    # components that select no plane: the reference leaves all-zero buffers (histogram.c:372-373)
+    res = engine.accumulate_host(f, settings=pkg.ScopeSettings(hist_components=0x00, wave_components=0x08))
+    assert res["hist"].sum() == 0 and res["wave"].sum() == 0 and res["vscope"].sum() > 0
+
+
+def test_tall_and_wide_extremes(engine, oracle, pkg):
+    """very tall (many tiles, u16 bins close to their limit is covered by 8K in the property tests),
+    very wide single row, width not a multiple of the strip, height not a multiple of the tile"""
+    for w, h in [(3, 5000), (4100, 1), (95, 129), (33, 65)]:
+        f = pkg.frames.random(w, h, seed=w + h)
+        yuv = oracle.rgb_to_yuv(f, 2)
+        st = pkg.ScopeSettings()
+        _check(engine.accumulate_host(f, settings=st), oracle, f, yuv, st, f"{w}x{h}")

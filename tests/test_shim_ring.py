@@ -99,3 +99,45 @@ def test_ring_orders_frames_and_drops_when_busy(shim, pkg):
     assert tags == sorted(tags) and tags[0] == 1 and 50 in tags
     assert cm.frames_processed == len(seen)
     lib.b200_cm_destroy(C.byref(cm))
+
+
+def test_roi_interleave_pacing(shim, pkg):
+    """n_interleave = 1 (the reference default): frames are staged on every other tick only."""
+    lib = shim
+    lib.b200_roi_target_render.restype = C.c_bool
+    lib.b200_roi_target_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                           C.c_uint32]
+    lib.b200_roi_tick.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+
+    class Roi(C.Structure):
+        _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("sources_mutex", C.c_byte * 40),
+                    ("his", C.c_void_p * 8), ("wvs", C.c_void_p * 8), ("vss", C.c_void_p * 8),
+                    ("n_his", C.c_int), ("n_wvs", C.c_int), ("n_vss", C.c_int), ("wave_tmp", C.c_void_p),
+                    ("wave_tmp_width", C.c_uint32), ("n_interleave", C.c_int), ("i_interleave", C.c_int),
+                    ("interleave_rendered", C.c_bool)]
+
+    roi = Roi()
+    lib.b200_roi_init(C.byref(roi), None, 1)
+    cm = C.create_string_buffer(4096)
+    lib.b200_cm_create(cm)
+    # flags = CONVERT_RGB: locate the field through the documented layout of the first test
+    flags_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16
+    seen = []
+    cfn = CB(lambda _d, sd: seen.append(int(C.cast(sd.contents.rgb_data, C.POINTER(C.c_uint8))[0])))
+    lib.b200_cm_request(cm, cfn, None)
+    C.c_uint32.from_buffer(cm, flags_off).value = 1
+    staged = []
+    for interleave in (1, 0):
+        roi.n_interleave, roi.i_interleave, roi.interleave_rendered = interleave, 0, False
+        for tick in range(8):
+            lib.b200_roi_tick(C.byref(roi), cm)
+            f = np.full((4, 64), 10 * interleave + tick, np.uint8)
+            before = C.c_int.from_buffer(cm, 3 * 56).value          # i_write_queue
+            lib.b200_roi_target_render(C.byref(roi), cm, f.ctypes.data, None, 64, 16, 4)
+            staged.append((interleave, tick, C.c_int.from_buffer(cm, 3 * 56).value != before))
+            lib.b200_cm_drain(cm)
+    on = [t for i, t, s in staged if i == 1 and s]
+    assert on == [0, 2, 4, 6]                                        # every other tick
+    assert all(s for i, t, s in staged if i == 0)                    # interleave off: every tick
+    lib.b200_cm_destroy(cm)
