@@ -127,8 +127,11 @@ struct scope_out_device {
  * increment.  min(sum of partials, 255) == the reference's saturating count. */
 struct scope_partial_device {
 	uint32_t *hist_counts; /* [1024]            additive */
-	uint32_t *wave_pairs;  /* [256][width][2]   u16x4 per (level, column): B,G | R,0 ; additive
-	                                            as int32 lanes while every u16 stays < 65536 */
+	uint32_t *wave_pairs;  /* [2][256][width]   plane 0: u16 pair (B|U, G|Y) per (level, column),
+	                                            plane 1: R|V; additive as int32 lanes while every
+	                                            u16 stays < 65536 (a frame has <= 65535 rows).  A
+	                                            waveform without the R|V channel never touches plane 1,
+	                                            so only plane 0 has to be reduced */
 	uint32_t *vscope_counts; /* [65536]         additive */
 };
 

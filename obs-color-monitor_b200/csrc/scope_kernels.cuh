@@ -59,7 +59,7 @@ struct StripParams {
 	uint32_t *chunk_counter;  // global work counter of this launch (zeroed by the host)
 	uint32_t *hist;           // [n][1024] u32, zeroed
 	uint8_t *wave;            // [n][256][out_width][4]
-	uint32_t *wave_pairs;     // partial: [256][out_width][2]
+	uint32_t *wave_pairs;     // partial: [2][256][out_width]: plane 0 = (B|U : lo16, G|Y : hi16), plane 1 = R|V
 	uint32_t *vscope_acc;     // [n][65536] u32, zeroed
 	unsigned long long hist_stride, wave_stride, vscope_stride; // elements between frames
 	Coef coef;
@@ -503,9 +503,9 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 			const size_t o = (size_t)(255 - v) * P.out_width + xo;
 			if (P.partial) {
 				if (mb | mg)
-					atomicAdd(P.wave_pairs + o * 2, mb | (mg << 16));
+					atomicAdd(P.wave_pairs + o, mb | (mg << 16));
 				if (mr)
-					atomicAdd(P.wave_pairs + o * 2 + 1, mr);
+					atomicAdd(P.wave_pairs + (size_t)256 * P.out_width + o, mr);
 			} else {
 				uint32_t *dst = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride);
 				dst[o] = min(mb, 255u) | (min(mg, 255u) << 8) | (min(mr, 255u) << 16);
@@ -973,15 +973,15 @@ __global__ void __launch_bounds__(256) wave_display_kernel(const uint8_t *wave, 
 						   (intensity_u8((w >> 16) & 0xFF, intensity) << 16);
 }
 
-// partial (tile-sharded) waveform: summed u16 pairs -> saturated u8 BGRX
+// partial (tile-sharded) waveform: summed u16 pairs (two planes) -> saturated u8 BGRX
 __global__ void __launch_bounds__(256) wave_pairs_finalize_kernel(const uint32_t *pairs, uint8_t *wave, size_t n_px)
 {
 	const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
 	if (i >= n_px)
 		return;
-	const uint2 w = reinterpret_cast<const uint2 *>(pairs)[i];
+	const uint32_t w0 = pairs[i], w1 = pairs[n_px + i];
 	reinterpret_cast<uint32_t *>(wave)[i] =
-		min(w.x & 0xFFFFu, 255u) | (min(w.x >> 16, 255u) << 8) | (min(w.y & 0xFFFFu, 255u) << 16);
+		min(w0 & 0xFFFFu, 255u) | (min(w0 >> 16, 255u) << 8) | (min(w1 & 0xFFFFu, 255u) << 16);
 }
 
 // test hook: the kernel's own transform for all 2^24 colours (index r<<16|g<<8|b)

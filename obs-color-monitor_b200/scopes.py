@@ -219,7 +219,7 @@ class ScopeEngine:
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         return {
             "hist": torch.zeros(1024, dtype=torch.int32, device=dev),
-            "wave_pairs": torch.zeros((256, full_width, 2), dtype=torch.int32, device=dev),
+            "wave_pairs": torch.zeros((2, 256, full_width), dtype=torch.int32, device=dev),
             "vscope": torch.zeros(65536, dtype=torch.int32, device=dev),
         }
 

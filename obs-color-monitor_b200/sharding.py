@@ -42,15 +42,21 @@ def col_bands(width: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def allreduce_partials(partial: Dict[str, "torch.Tensor"], keys=("hist", "wave_pairs", "vscope"), group=None):
+def allreduce_partials(partial: Dict[str, "torch.Tensor"], keys=("hist", "wave_pairs", "vscope"), group=None,
+                       wave_planes: int = 2):
     """In-place sum of the partial accumulators over all ranks.  The tensors are int32 views of
     u32 counts / u16x2 pairs: every lane stays below 2^31 (hist: <= W*H, pairs: each u16 half
     <= rows of the whole frame <= 65535, vscope: <= W*H), so integer addition is exact and carries
     never cross a u16 half."""
     import torch.distributed as dist
 
-    works = [dist.all_reduce(partial[k], op=dist.ReduceOp.SUM, group=group, async_op=True) for k in keys
-             if k in partial]
+    works = []
+    for k in keys:
+        if k not in partial:
+            continue
+        # waveform plane 1 only holds the R|V channel: skip it when that channel is off
+        t = partial[k][:wave_planes] if k == "wave_pairs" else partial[k]
+        works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
     for w in works:
         w.wait()
     return partial
@@ -105,17 +111,38 @@ class TiledFrame:
             self.engine.accumulate_partial(band, self.partial, x_offset=a, full_width=self.width,
                                            settings=self.settings, width=(b - a) if width is None else width)
 
-    def reduce_and_finalize(self):
+    def _reduce_keys(self):
         from ._ffi import SCOPE_HIST, SCOPE_VSCOPE, SCOPE_WAVE
 
+        keys = []
+        if self.settings.scopes & SCOPE_HIST:
+            keys.append("hist")
+        if self.settings.scopes & SCOPE_WAVE:
+            keys.append("wave_pairs")       # cols mode: disjoint columns, the sum just merges them
+        if self.settings.scopes & SCOPE_VSCOPE:
+            keys.append("vscope")
+        return keys
+
+    def start_reduce(self):
+        """Enqueue the all-reduce of this frame's partials without waiting for it, so the caller
+        can accumulate the next frame (into another TiledFrame) while NCCL runs."""
+        import torch.distributed as dist
+
+        self._works = []
         if self.world > 1:
-            keys = []
-            if self.settings.scopes & SCOPE_HIST:
-                keys.append("hist")
-            if self.settings.scopes & SCOPE_WAVE:
-                keys.append("wave_pairs")       # cols mode: disjoint columns, the sum just merges them
-            if self.settings.scopes & SCOPE_VSCOPE:
-                keys.append("vscope")
-            allreduce_partials(self.partial, keys, self.group)
+            planes = 2 if (self.settings.wave_components & 0x44) else 1
+            for k in self._reduce_keys():
+                t = self.partial[k][:planes] if k == "wave_pairs" else self.partial[k]
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for start_reduce() (stream-side) and saturate into the reference layouts."""
+        for w in getattr(self, "_works", []):
+            w.wait()
+        self._works = []
         return self.engine.finalize_partial(self.partial, full_width=self.width, full_height=self.height,
                                             settings=self.settings)
+
+    def reduce_and_finalize(self):
+        self.start_reduce()
+        return self.finish()

@@ -41,13 +41,13 @@ def _oracle_partials(orc, f, yuv, y0, y1, x0, x1, full_width):
     hist = orc.histogram_counts(0x07, tile, tyuv).astype(np.int32)
     # unsaturated per-column counts, packed as u16 pairs (B,G | R,0)
     h, w = tile.shape[:2]
-    pairs = np.zeros((256, full_width, 2), np.int32)
+    pairs = np.zeros((2, 256, full_width), np.int32)
     for c, (word, shift) in enumerate([(0, 0), (0, 16), (1, 0)]):
         cnt = np.zeros((256, w), np.int64)
         a = tile[..., 3] != 0
         for x in range(w):
             cnt[:, x] = np.bincount(tile[a[:, x], x, c], minlength=256)
-        pairs[::-1, x0:x1, word] += (cnt << shift).astype(np.int32)   # row 0 = value 255
+        pairs[word, ::-1, x0:x1] += (cnt << shift).astype(np.int32)   # row 0 = value 255
     vs = np.zeros(65536, np.int32)
     idx = tyuv[..., 0].astype(np.int64) + 256 * (255 - tyuv[..., 2].astype(np.int64))
     vs += np.bincount(idx.ravel(), minlength=65536).astype(np.int32)
@@ -74,9 +74,9 @@ def _worker(rank, world, port, mode, q):
     # finalize exactly like wave_pairs_finalize_kernel / vscope_finalize_kernel
     pr = partial["wave_pairs"].numpy().view(np.uint32)
     wave = np.zeros((256, w, 4), np.uint8)
-    wave[..., 0] = np.minimum(pr[..., 0] & 0xFFFF, 255)
-    wave[..., 1] = np.minimum(pr[..., 0] >> 16, 255)
-    wave[..., 2] = np.minimum(pr[..., 1] & 0xFFFF, 255)
+    wave[..., 0] = np.minimum(pr[0] & 0xFFFF, 255)
+    wave[..., 1] = np.minimum(pr[0] >> 16, 255)
+    wave[..., 2] = np.minimum(pr[1] & 0xFFFF, 255)
     vsc = np.minimum(partial["vscope"].numpy(), 255).astype(np.uint8).reshape(256, 256)
     ok = (np.array_equal(partial["hist"].numpy().view(np.uint32), orc.histogram_counts(0x07, f, yuv))
           and np.array_equal(wave, orc.waveform(0x07, f, yuv)) and np.array_equal(vsc, orc.vectorscope(yuv)))
