@@ -24,9 +24,16 @@
 namespace scope {
 
 constexpr int kStripPx = 32;          // columns per strip == lanes per warp
-constexpr int kTileRows = 64;         // rows per TMA tile
-constexpr int kTmaWarps = 16;         // consumer warps of the TMA kernel (4 rows of each tile per warp)
-constexpr int kMaxStages = 4;         // depth of the tile ring (what the bins leave room for)
+#ifndef SCOPE_TILE_ROWS
+#define SCOPE_TILE_ROWS 64
+#endif
+#ifndef SCOPE_TMA_WARPS
+#define SCOPE_TMA_WARPS 16
+#endif
+constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile
+constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernel (kTileRows / kTmaWarps rows each)
+constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
+constexpr int kMaxStages = 8;              // upper bound of the ring depth (barrier storage)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
 constexpr int kMaxChunkItems = 10;    // upper bound of strips per dynamically claimed chunk
 constexpr int kQueue = 4;             // chunk-id mailbox entries (producer is < kQueue chunks ahead)
@@ -239,7 +246,12 @@ struct SmemLayout {
 	static constexpr int kStageOff = kWave0Off + kWaveBytes;
 	static constexpr int kStageBytes = USE_TMA ? kPlanes * kTileBytes : 0;
 	// two planes per stage (surface mode) leave room for a 2-deep ring only
-	static constexpr int kStages = kPlanes == 2 ? 2 : kMaxStages;
+	// as many stages as fit (two planes per stage in surface mode halve the depth)
+	static constexpr int kStagesFit = USE_TMA ? kRingBytes / (kPlanes * kTileBytes) : 1;
+	static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : (kStagesFit < 2 ? 2 : kStagesFit);
+#ifndef SCOPE_EXPERIMENT
+	static_assert(!USE_TMA || kStagesFit >= 2, "tile too large for the ring");
+#endif
 	static constexpr int kBarOff = kStageOff + kStages * kStageBytes;
 	static constexpr int kQueueOff = kBarOff + (USE_TMA ? 2 * kMaxStages * 8 : 0);
 	static constexpr int kTotal = kQueueOff + (USE_TMA ? kQueue * 4 : 0) + 16;
