@@ -310,8 +310,7 @@ __device__ __forceinline__ void vs_undo(const VsAdd &a)
 
 // ---------------------------------------------------------------------------
 // one thread's share of a tile: N vertically adjacent pixels of its column.
-// FAST = the tile lies completely inside the frame and all three channels are accumulated:
-// no per-pixel validity logic at all.
+// FAST = the tile lies completely inside the frame: no per-pixel validity logic at all.
 // ---------------------------------------------------------------------------
 struct TileCtx {
 	uint32_t vs_base, wb0, wb1, magic, bins_mask;
@@ -605,15 +604,22 @@ template <int SRC, bool VSCOPE, bool SURFACE, int N>
 __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 {
 	if (SRC != SRC_NONE) {
-		if (o.all_counted) {
+		if (o.all_counted && c.bins_mask == 7u) {
 #pragma unroll
 			for (int k = 0; k < N; k++)
 				bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, 1u);
 		} else {
+			// some pixels transparent, or only some channels wanted (uniform branches)
 #pragma unroll
-			for (int k = 0; k < N; k++)
-				bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1,
-							   o.a[k] > 0x00FFFFFFu ? 1u : 0u);
+			for (int k = 0; k < N; k++) {
+				const uint32_t one = (o.all_counted || o.a[k] > 0x00FFFFFFu) ? 1u : 0u;
+				if (c.bins_mask & 1u)
+					bins_add<true, false, false>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, one);
+				if (c.bins_mask & 2u)
+					bins_add<false, true, false>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, one);
+				if (c.bins_mask & 4u)
+					bins_add<false, false, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, one);
+			}
 		}
 	}
 	if (VSCOPE) {
@@ -621,17 +627,22 @@ __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 			if (c.lane == 0)
 				vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
 		} else {
-			VsAdd a[N];
-			uint32_t any = 0;
+			// N adds in flight; their old words are OR-ed and tested once for "some half
+			// already >= 0x8000" (either half: a false alarm only costs the exact re-check)
+			uint32_t old[N], any = 0;
 #pragma unroll
 			for (int k = 0; k < N; k++) {
-				a[k] = vs_add(c.vs_base, o.idx[k], 1u);
-				any |= a[k].sat;
+				const uint32_t h = o.idx[k] >> 15;
+				old[k] = atom_shared_add((o.idx[k] & 0x7FFFu) * 4u + c.vs_base, h * 0xFFFFu + 1u);
+				any |= old[k];
 			}
-			if (any) {
+			if (any & 0x80008000u) {
 #pragma unroll
-				for (int k = 0; k < N; k++)
-					vs_undo(a[k]);
+				for (int k = 0; k < N; k++) {
+					const uint32_t h = o.idx[k] >> 15;
+					if (old[k] & (h * 0x7FFF8000u + 0x8000u))
+						red_shared((o.idx[k] & 0x7FFFu) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
+				}
 			}
 		}
 	}
@@ -727,7 +738,6 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
 			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
-	const bool fast_cfg = P.bins_mask == 7u;
 	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
 	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
 	uint32_t stage = 0, phase = 0, qr = 0;
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 			const bool strip_full = strip * kStripPx + kStripPx <= P.width;
 
 			// tiles [0, n_full) lie completely inside the frame (uniform over the CTA)
-			const uint32_t n_full = (strip_full && fast_cfg) ? P.height / kTileRows : 0u;
+			const uint32_t n_full = strip_full ? P.height / kTileRows : 0u;
 			bool skip_wait = item == first; // the chunk announcement already waited for tile 0
 			// fetch = wait for the tile, read this thread's pixels, remember which stage to hand back
 			auto fetch_tile = [&](uint32_t(&p)[RPW], uint32_t(&q)[RPW]) -> uint32_t {
