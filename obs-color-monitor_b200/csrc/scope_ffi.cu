@@ -96,14 +96,30 @@ int fail(scope_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess
 			return fail(ctx, SCOPE_ERR_CUDA, #call, e_);   \
 	} while (0)
 
+// 10^6 x the coefficients printed in data/common.effect:27-29 (BT.601) and :38-40 (BT.709), as
+// integers, order R, G, B; K = floor(10^6 * (255 * off + 1/2)) with off = 1/2 - 1/256 (U), 0 (Y),
+// 1/2 (V).  The kernel multiplies carriers (0x4B000000 + byte), so the bias they add is taken out
+// of K here (mod 2^32).
 Coef coef_for(int colorspace)
 {
-	// data/common.effect:27-29 (601) and :38-40 (709); anything but 1 means 709 (util.c:25-41)
-	if (colorspace == 1)
-		return Coef{-0.147643f, -0.289855f, +0.437500f, +0.299000f, +0.587000f,
-			    +0.114000f, +0.437500f, -0.366351f, -0.071147f};
-	return Coef{-0.100643f, -0.338571f, +0.439216f, +0.212600f, +0.715200f,
-		    +0.072200f, +0.439216f, -0.398941f, -0.040273f};
+	static const int32_t k601[3][3] = {{-147643, -289855, +437500}, {+299000, +587000, +114000},
+					   {+437500, -366351, -71147}};
+	static const int32_t k709[3][3] = {{-100643, -338571, +439216}, {+212600, +715200, +72200},
+					   {+439216, -398941, -40273}};
+	static const uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
+	const int32_t(*m)[3] = colorspace == 1 ? k601 : k709;
+	Coef c;
+	uint32_t *rows[3] = {c.u, c.y, c.v};
+	uint32_t *adds[3] = {&c.ku, &c.ky, &c.kv};
+	for (int ch = 0; ch < 3; ch++) {
+		uint32_t sum = 0;
+		for (int i = 0; i < 3; i++) {
+			rows[ch][i] = (uint32_t)m[ch][i];
+			sum += (uint32_t)m[ch][i];
+		}
+		*adds[ch] = k_add[ch] - sum * 0x4B000000u;
+	}
+	return c;
 }
 
 // components -> (source plane, channel mask) exactly like histogram.c:367-377 / waveform.c:228-238
@@ -163,6 +179,20 @@ bool pick_kernel2(int src, bool vs, bool tma, KernelChoice &k)
 
 bool pick_kernel(int src, bool vs, bool surface, bool tma, KernelChoice &k)
 {
+	// experiment kept for A/B runs (profiles/ubench_r01.md): SCOPE_SPLIT=1 selects the
+	// warp-specialised kernel for the headline combination; it measured no faster
+	const char *split = getenv("SCOPE_SPLIT");
+	if (tma && vs && src == SRC_RGB && split && split[0] == '1') {
+		if (surface) {
+			k.tma = scope_strip_kernel_split<true>;
+			k.smem = SmemLayout<SRC_RGB, true, true, true>::kTotal;
+		} else {
+			k.tma = scope_strip_kernel_split<false>;
+			k.smem = SmemLayout<SRC_RGB, true, false, true>::kTotal;
+		}
+		k.threads = (kSplitVsWarps + kSplitBinWarps) * 32 + 32;
+		return true;
+	}
 	return surface ? pick_kernel2<true>(src, vs, tma, k) : pick_kernel2<false>(src, vs, tma, k);
 }
 
@@ -288,13 +318,12 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	if (grid > P.items)
 		grid = P.items;
 	if (use_tma) {
-		// chunks of strips are claimed at run time from a zeroed counter: big enough to keep
-		// vectorscope flushes rare, small enough that every CTA gets >= ~6 of them
+		// chunks of strips are claimed at run time from a zeroed counter (guided
+		// self-scheduling in tma_produce): at most chunk_items strips each - big enough to keep
+		// vectorscope flushes rare, small enough that every CTA gets >= ~6 of them - and
+		// shrinking towards the end of the batch
 		uint32_t ch = P.items / (grid * 6u);
 		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
-		const uint32_t n_chunks = (P.items + P.chunk_items - 1) / P.chunk_items;
-		if (grid > n_chunks)
-			grid = n_chunks;
 		if (!ctx->d_counters)
 			CU_TRY(ctx, cudaMalloc(&ctx->d_counters, 256 * sizeof(uint32_t)));
 		P.chunk_counter = ctx->d_counters + (ctx->counter_next++ & 255u);

@@ -32,11 +32,19 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #endif
 constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile
 constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernel (kTileRows / kTmaWarps rows each)
+#ifndef SCOPE_SPLIT_VS_WARPS
+#define SCOPE_SPLIT_VS_WARPS 16
+#endif
+#ifndef SCOPE_SPLIT_BIN_WARPS
+#define SCOPE_SPLIT_BIN_WARPS 8
+#endif
+constexpr int kSplitVsWarps = SCOPE_SPLIT_VS_WARPS;   // specialised kernel: warps doing transform + vectorscope
+constexpr int kSplitBinWarps = SCOPE_SPLIT_BIN_WARPS; // specialised kernel: warps doing the column bins
 constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
 constexpr int kMaxStages = 8;              // upper bound of the ring depth (barrier storage)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
 constexpr int kMaxChunkItems = 10;    // upper bound of strips per dynamically claimed chunk
-constexpr int kQueue = 4;             // chunk-id mailbox entries (producer is < kQueue chunks ahead)
+constexpr int kQueue = 4;             // chunk mailbox entries {first strip, count} (producer is < kQueue chunks ahead)
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
 constexpr int kVsWords = 32768;       // 65536 vectorscope bins, two u16 per word
@@ -44,8 +52,11 @@ constexpr int kWaveWords = 256 * 32;  // one plane: [level][lane]
 
 enum : int { SRC_NONE = 0, SRC_RGB = 1, SRC_YUV = 2 };
 
+// colour transform constants: 10^6 x the effect file's coefficients, order R, G, B, and the
+// rounding/offset constants with the carrier bias folded in (scope_ffi.cu: coef_for)
 struct Coef {
-	float u0, u1, u2, y0, y1, y2, v0, v1, v2;
+	uint32_t u[3], y[3], v[3];
+	uint32_t ku, ky, kv;
 };
 
 struct StripParams {
@@ -125,51 +136,11 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
 	return v;
 }
 
-// ---- packed fp32x2 (sm_100a FMUL2 / FFMA2 / FADD2): two pixels per instruction ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi)
-{
-	f32x2 r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, uint32_t &lo, uint32_t &hi)
-{
-	asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-	f32x2 r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-	return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 splat2(float c)
-{
-	return pack2(c, c);
-}
-
 // ---------------------------------------------------------------------------
 // "carriers": a byte b travels as the bit pattern 0x4B0000bb, i.e. the float 2^23 + b.
 //   * PRMT makes one from a pixel byte in a single instruction;
-//   * the colour transform ends in such a pattern (add.rz with 2^23);
+//   * integer multiply-adds on carriers differ from those on the bytes by a constant that
+//     folds into the addend (the colour transform below);
 //   * (carrier << 7) + (base - 0x80000000) == base + 128*b   (0x4B000000 << 7 = 0x80000000
 //     mod 2^32), so a waveform bin address is ONE multiply-add away from a carrier.
 // ---------------------------------------------------------------------------
@@ -186,49 +157,45 @@ __device__ __forceinline__ uint32_t carrier(uint32_t pixel, uint32_t magic)
 	return r;
 }
 
-// carriers of two pixels -> exact floats b (subtract 2^23), packed
-__device__ __forceinline__ f32x2 carriers_to_f32x2(uint32_t ca, uint32_t cb)
+// RGB -> YUV (data/common.effect:23-43), pinned as the EXACT value of the shader's expression
+// rounded the way a UNORM8 render target rounds (oracle/scope_oracle.c):
+//   q = floor(c0*R + c1*G + c2*B + 255*off + 1/2)       (bytes in, real arithmetic)
+// The effect file's coefficients have six decimals, so with c' = 10^6 c the sum
+//   S = c0'*R + c1'*G + c2'*B + K'    (K' = floor(10^6 (255 off + 1/2)), 0 <= S < 2^28)
+// is an exact integer and q = floor(S / 10^6) = (S * ceil(2^48 / 10^6)) >> 48 for every S < 2^28
+// (the usual multiply-high division; checked for all 2^24 colours in tests/test_oracle.py).
+// The high word of that product is q * 2^16 + fraction: q sits in BYTE 2, where one PRMT picks it
+// up.  The three multiply-adds run on the CARRIERS (0x4B000000 + byte): the extra
+// 0x4B000000 * (c0'+c1'+c2') is folded into K' on the host, mod 2^32.
+constexpr uint32_t kDivMagic = 281474977u; // ceil(2^48 / 10^6)
+
+__device__ __forceinline__ uint32_t yuv_channel(const uint32_t (&bgr)[3], const uint32_t (&c)[3], uint32_t k)
 {
-	return add2(pack2(__uint_as_float(ca), __uint_as_float(cb)), splat2(-8388608.0f));
+	uint32_t s = bgr[2] * c[0] + k;
+	s = bgr[1] * c[1] + s;
+	s = bgr[0] * c[2] + s;
+	return __umulhi(s, kDivMagic);
 }
 
-// x / 255 correctly rounded for x in {0..255}: fma(x, k0, rn(x*k1)), k0 = rn(1/255),
-// k1 = rn(1/255 - k0).  Checked against IEEE division for all 256 inputs
-// (tests/test_oracle.py::test_div255_constants) and, through the kernel, for all 2^24 colours.
-__device__ __forceinline__ f32x2 div255(f32x2 x)
-{
-	const f32x2 k0 = splat2(__uint_as_float(0x3B808081u)); // 0x1.010102p-8
-	const f32x2 k1 = splat2(__uint_as_float(0xAF7EFEFFu)); // -0x1.fdfdfep-33
-	return fma2(x, k0, mul2(x, k1));
-}
-
-// one output channel for two pixels: p = c0*r; p = fma(c1,g,p); p = fma(c2,b,p); t = p + off;
-// q = floor(fma(t, 255, 0.5)).  Returns the two CARRIERS of q (floats 2^23 + q).  The [0,1]
-// clamp of the definition never acts (exhaustively verified, tests/test_oracle.py).
-__device__ __forceinline__ void yuv_channel(f32x2 r, f32x2 g, f32x2 b, float c0, float c1, float c2, float off,
-					    uint32_t &qa, uint32_t &qb)
-{
-	f32x2 p = mul2(splat2(c0), r);
-	p = fma2(splat2(c1), g, p);
-	p = fma2(splat2(c2), b, p);
-	p = add2(p, splat2(off));
-	p = fma2(p, splat2(255.0f), splat2(0.5f));
-	unpack2(add2_rz(p, splat2(8388608.0f)), qa, qb);
-}
-
-// RGB carriers of two pixels -> U/(Y)/V carriers (data/common.effect:23-43 as pinned in
-// oracle/scope_oracle.c).
+// B, G, R carriers of one pixel -> U, (Y), V, each in byte 2 of its word (bytes 3 = 0)
 template <bool NEED_Y>
-__device__ __forceinline__ void rgb_to_yuv_pair(const uint32_t (&ca)[3], const uint32_t (&cb)[3], const Coef &c,
-						 uint32_t (&ya)[3], uint32_t (&yb)[3])
+__device__ __forceinline__ void rgb_to_yuv_hi(const uint32_t (&bgr)[3], const Coef &c, uint32_t (&hi)[3])
 {
-	const f32x2 b = div255(carriers_to_f32x2(ca[0], cb[0]));
-	const f32x2 g = div255(carriers_to_f32x2(ca[1], cb[1]));
-	const f32x2 r = div255(carriers_to_f32x2(ca[2], cb[2]));
-	yuv_channel(r, g, b, c.u0, c.u1, c.u2, 0.5f - 1.0f / 256.0f, ya[0], yb[0]);
-	if (NEED_Y)
-		yuv_channel(r, g, b, c.y0, c.y1, c.y2, 0.0f, ya[1], yb[1]);
-	yuv_channel(r, g, b, c.v0, c.v1, c.v2, 0.5f, ya[2], yb[2]);
+	hi[0] = yuv_channel(bgr, c.u, c.ku);
+	hi[1] = NEED_Y ? yuv_channel(bgr, c.y, c.ky) : 0u;
+	hi[2] = yuv_channel(bgr, c.v, c.kv);
+}
+
+// the same, as carriers of U, Y, V
+template <bool NEED_Y>
+__device__ __forceinline__ void rgb_to_yuv_carriers(const uint32_t (&bgr)[3], const Coef &c, uint32_t magic,
+						     uint32_t (&yuv)[3])
+{
+	uint32_t hi[3];
+	rgb_to_yuv_hi<NEED_Y>(bgr, c, hi);
+	yuv[0] = carrier<2>(hi[0], magic);
+	yuv[1] = NEED_Y ? carrier<2>(hi[1], magic) : 0u;
+	yuv[2] = carrier<2>(hi[2], magic);
 }
 
 // ---------------------------------------------------------------------------
@@ -254,7 +221,7 @@ struct SmemLayout {
 #endif
 	static constexpr int kBarOff = kStageOff + kStages * kStageBytes;
 	static constexpr int kQueueOff = kBarOff + (USE_TMA ? 2 * kMaxStages * 8 : 0);
-	static constexpr int kTotal = kQueueOff + (USE_TMA ? kQueue * 4 : 0) + 16;
+	static constexpr int kTotal = kQueueOff + (USE_TMA ? kQueue * 8 : 0) + 16;
 };
 
 // ---------------------------------------------------------------------------
@@ -289,6 +256,20 @@ __device__ __forceinline__ void bins_add(uint32_t cb, uint32_t cg, uint32_t cr, 
 // calls vs_undo.  An add that found its bin at >= 0x8000 is taken back, so a half can never
 // wrap 16 bits, and a bin that ever reached 0x8000 keeps a value far above 255: it saturates
 // to 255 at the end exactly like the reference's `if (*c < 255) ++*c`.
+//
+// Bank swizzle.  The plain word index U + 256 (V & 127) puts every bin of one U column in the
+// same bank (bank = U mod 32), and picture content has few distinct U values per 32-pixel row
+// segment: simulated on the "natural" test frames one warp-wide atomic then costs 11.3
+// conflict passes.  Replacing the low five bits by (U + 4 V) mod 32 spreads neighbouring
+// (U, V) pairs over the banks (4.9 passes, the floor set by lanes that hit the very SAME bin);
+// random content is unchanged (3.5).  For fixed V the map is a rotation of U's low bits, so it
+// is a bijection on the 15-bit word index; flush_vscope undoes it.
+__device__ __forceinline__ uint32_t vs_word(uint32_t idx)
+{
+	const uint32_t t = (idx >> 8) * 4u + idx; // low 5 bits: (U + 4 V) mod 32
+	return (idx & 0x7FE0u) | (t & 31u);
+}
+
 struct VsAdd {
 	uint32_t addr, add, sat;
 };
@@ -296,7 +277,7 @@ __device__ __forceinline__ VsAdd vs_add(uint32_t vs_base, uint32_t idx, uint32_t
 {
 	VsAdd r;
 	const uint32_t h = idx >> 15;            // 0: lower half (V < 128), 1: upper half
-	r.addr = (idx & 0x7FFFu) * 4u + vs_base;
+	r.addr = vs_word(idx) * 4u + vs_base;
 	r.add = h * (k * 0xFFFFu) + k;           // k << 16 for the upper half, k for the lower
 	const uint32_t old = atom_shared_add(r.addr, r.add);
 	r.sat = old & (h * 0x7FFF8000u + 0x8000u);
@@ -321,7 +302,6 @@ template <int SRC, bool VSCOPE, bool SURFACE, bool FAST, int N>
 __device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef, const uint32_t (&p)[N],
 					     const uint32_t (&q)[N], const bool (&ok)[N])
 {
-	static_assert(N % 2 == 0, "pixels are transformed in packed pairs");
 	constexpr bool kTransform = !SURFACE && (VSCOPE || SRC == SRC_YUV);
 	uint32_t crgb[N][3]; // carriers of B, G, R
 	uint32_t cyuv[N][3]; // carriers of U, Y, V
@@ -335,8 +315,8 @@ __device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef,
 	}
 	if (kTransform) {
 #pragma unroll
-		for (int k = 0; k < N; k += 2)
-			rgb_to_yuv_pair<SRC == SRC_YUV>(crgb[k], crgb[k + 1], coef, cyuv[k], cyuv[k + 1]);
+		for (int k = 0; k < N; k++)
+			rgb_to_yuv_carriers<SRC == SRC_YUV>(crgb[k], coef, c.magic, cyuv[k]);
 	} else if (SURFACE && SRC == SRC_YUV) {
 #pragma unroll
 		for (int k = 0; k < N; k++) {
@@ -462,8 +442,10 @@ __device__ __forceinline__ void flush_vscope(const StripParams &P, uint32_t *vs,
 		uint4 w = reinterpret_cast<uint4 *>(vs)[i];
 		if ((w.x | w.y | w.z | w.w) != 0u) {
 			const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-			const uint32_t word = i * 4; // = U | (V & 0x7F) << 8
-			const uint32_t u = word & 0xFFu, v7 = word >> 8;
+			// word = vs_word(U | V << 8): undo the bank swizzle (the four words of this
+			// uint4 stay four consecutive U values: the rotation is a multiple of 4)
+			const uint32_t word = i * 4;
+			const uint32_t v7 = word >> 8, u = (word & 0xE0u) | ((word - v7 * 4u) & 31u);
 			uint32_t *lo = acc + (255u - v7) * 256u + u; // V = v7
 			uint32_t *hi = acc + (127u - v7) * 256u + u; // V = v7 | 0x80
 #pragma unroll
@@ -547,7 +529,8 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 					     const uint32_t (&q)[N], Prep<N> &o)
 {
 	constexpr bool kTransform = !SURFACE && (VSCOPE || SRC == SRC_YUV);
-	uint32_t crgb[N][3], cyuv[N][3];
+	uint32_t crgb[N][3]; // carriers of B, G, R
+	uint32_t hi[N][3];   // transform results: U, Y, V in byte 2
 	if (SRC == SRC_RGB || kTransform) {
 #pragma unroll
 		for (int k = 0; k < N; k++) {
@@ -558,23 +541,24 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 	}
 	if (kTransform) {
 #pragma unroll
-		for (int k = 0; k < N; k += 2)
-			rgb_to_yuv_pair<SRC == SRC_YUV>(crgb[k], crgb[k + 1], coef, cyuv[k], cyuv[k + 1]);
-	} else if (SURFACE && SRC == SRC_YUV) {
-#pragma unroll
-		for (int k = 0; k < N; k++) {
-			cyuv[k][0] = carrier<0>(q[k], c.magic);
-			cyuv[k][1] = carrier<1>(q[k], c.magic);
-			cyuv[k][2] = carrier<2>(q[k], c.magic);
-		}
+		for (int k = 0; k < N; k++)
+			rgb_to_yuv_hi<SRC == SRC_YUV>(crgb[k], coef, hi[k]);
 	}
 	o.all_counted = true;
 	if (SRC != SRC_NONE) {
 #pragma unroll
 		for (int k = 0; k < N; k++) {
-			o.cs[k][0] = SRC == SRC_RGB ? crgb[k][0] : cyuv[k][0];
-			o.cs[k][1] = SRC == SRC_RGB ? crgb[k][1] : cyuv[k][1];
-			o.cs[k][2] = SRC == SRC_RGB ? crgb[k][2] : cyuv[k][2];
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				if (SRC == SRC_RGB)
+					o.cs[k][j] = crgb[k][j];
+				else if (SURFACE)
+					o.cs[k][j] = j == 0   ? carrier<0>(q[k], c.magic)
+						     : j == 1 ? carrier<1>(q[k], c.magic)
+							      : carrier<2>(q[k], c.magic);
+				else
+					o.cs[k][j] = carrier<2>(hi[k][j], c.magic);
+			}
 		}
 		if (SRC == SRC_RGB || SURFACE) {
 			uint32_t m = 0xFFFFFFFFu;
@@ -590,7 +574,7 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 	if (VSCOPE) {
 #pragma unroll
 		for (int k = 0; k < N; k++)
-			o.idx[k] = SURFACE ? __byte_perm(q[k], 0u, 0x4420) : __byte_perm(cyuv[k][0], cyuv[k][2], 0x1140);
+			o.idx[k] = SURFACE ? __byte_perm(q[k], 0u, 0x4420) : __byte_perm(hi[k][0], hi[k][2], 0x3362);
 		bool same = true;
 #pragma unroll
 		for (int k = 1; k < N; k++)
@@ -633,7 +617,7 @@ __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 #pragma unroll
 			for (int k = 0; k < N; k++) {
 				const uint32_t h = o.idx[k] >> 15;
-				old[k] = atom_shared_add((o.idx[k] & 0x7FFFu) * 4u + c.vs_base, h * 0xFFFFu + 1u);
+				old[k] = atom_shared_add(vs_word(o.idx[k]) * 4u + c.vs_base, h * 0xFFFFu + 1u);
 				any |= old[k];
 			}
 			if (any & 0x80008000u) {
@@ -641,7 +625,7 @@ __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 				for (int k = 0; k < N; k++) {
 					const uint32_t h = o.idx[k] >> 15;
 					if (old[k] & (h * 0x7FFF8000u + 0x8000u))
-						red_shared((o.idx[k] & 0x7FFFu) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
+						red_shared(vs_word(o.idx[k]) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
 				}
 			}
 		}
@@ -649,89 +633,76 @@ __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 }
 
 // ---------------------------------------------------------------------------
-// strip kernel, TMA loader.  A producer warp (one elected lane) walks CHUNKS of P.chunk_items
-// consecutive strips, claimed from a global counter so that fast and slow frame content
-// balances across CTAs, and fills a kStages-deep shared-memory ring of 64-row x 128-byte
-// tiles with cp.async.bulk.tensor.  16 consumer warps take 4 rows of every tile each.
-// The chunk id travels to the consumers through a small shared-memory queue that is written
-// before the chunk's first tile is armed (mbarrier release/acquire orders it).
+// TMA loader, shared by the two TMA kernels below.
+// A producer warp (one elected lane) walks CHUNKS of up to P.chunk_items consecutive strips,
+// claimed from a global counter so that fast and slow frame content balances across CTAs, and fills a
+// kStages-deep shared-memory ring of 64-row x 128-byte tiles with cp.async.bulk.tensor.  The
+// chunk id travels to the consumers through a small shared-memory queue that is written before
+// the chunk's first tile is armed (mbarrier release/acquire orders it).
 // ---------------------------------------------------------------------------
-template <int SRC, bool VSCOPE, bool SURFACE>
-__global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
-	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
-			       const __grid_constant__ CUtensorMap map_yuv)
+template <class L>
+__device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensorMap *map_rgb,
+					    const CUtensorMap *map_yuv, uint32_t smem_base,
+					    volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty)
 {
-	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
-	constexpr int NW = kTmaWarps, RPW = kTileRows / NW;
 	constexpr int kStages = L::kStages;
-	extern __shared__ __align__(128) uint8_t smem[];
-	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
-	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
-	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff); // kQueue entries
-	const uint32_t smem_base = smem_u32(smem);
-	const uint32_t bar_full = smem_base + L::kBarOff;     // kStages x 8 B
-	const uint32_t bar_empty = bar_full + kMaxStages * 8; // kStages x 8 B
-
-	const int tid = threadIdx.x;
-	const int warp = tid >> 5, lane = tid & 31;
-	const bool is_producer = warp == NW;
-
-	if (!is_producer)
-		zero_bins<NW>(vs, wave0, VSCOPE, SRC != SRC_NONE, tid);
-	if (tid == 0) {
-		for (int s = 0; s < kStages; s++) {
-			mbar_init(bar_full + 8 * s, 1);
-			mbar_init(bar_empty + 8 * s, NW);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
 	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
-	const uint32_t n_chunks = (P.items + P.chunk_items - 1) / P.chunk_items;
-
-	if (is_producer) {
-		// ================= TMA producer (one elected lane) =================
-		if (lane == 0) {
-			uint32_t stage = 0, phase = 0, qw = 0;
-			for (;;) {
-				const uint32_t chunk = atomicAdd(P.chunk_counter, 1u);
-				const bool done = chunk >= n_chunks;
-				// announce the chunk (or the end) before its first tile can complete
-				mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-				chunk_q[qw % kQueue] = done ? 0xFFFFFFFFu : chunk;
-				qw++;
-				if (done) {
-					mbar_arrive(bar_full + 8 * stage); // wake the consumers with no data
-					break;
-				}
-				const uint32_t first = chunk * P.chunk_items, last = min(first + P.chunk_items, P.items);
-				for (uint32_t item = first; item < last; item++) {
-					const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
-					const int x = (int)(strip * kStripPx);
-					for (uint32_t t = 0; t < tiles; t++) {
-						if (!(item == first && t == 0))
-							mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-						const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
-						mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
-						if (L::kLoadRgb)
-							tma_load_3d(dst, &map_rgb, bar_full + 8 * stage, x, (int)(t * kTileRows),
-								    (int)frame);
-						if (L::kLoadYuv)
-							tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), &map_yuv,
-								    bar_full + 8 * stage, x, (int)(t * kTileRows), (int)frame);
-						if (++stage == kStages) {
-							stage = 0;
-							phase ^= 1;
-						}
-					}
+	uint32_t stage = 0, phase = 0, qw = 0;
+	for (;;) {
+		// guided self-scheduling: take 1/(2 x grid) of what is left (at most chunk_items
+		// strips, at least one), so chunks shrink towards the end of the batch and the CTAs
+		// finish together.  `seen` may be stale; only the size of the claim depends on it.
+		const uint32_t seen = *reinterpret_cast<volatile const uint32_t *>(P.chunk_counter);
+		uint32_t want = seen < P.items ? (P.items - seen) / (2u * gridDim.x) : 1u;
+		want = min(max(want, 1u), P.chunk_items);
+		const uint32_t first = atomicAdd(P.chunk_counter, want);
+		const bool done = first >= P.items;
+		const uint32_t last = min(first + want, P.items);
+		// announce the chunk (or the end) before its first tile can complete
+		mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+		chunk_q[2 * (qw % kQueue)] = first;
+		chunk_q[2 * (qw % kQueue) + 1] = done ? 0u : last - first;
+		qw++;
+		if (done) {
+			mbar_arrive(bar_full + 8 * stage); // wake the consumers with no data
+			break;
+		}
+		for (uint32_t item = first; item < last; item++) {
+			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
+			const int x = (int)(strip * kStripPx);
+			for (uint32_t t = 0; t < tiles; t++) {
+				if (!(item == first && t == 0))
+					mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+				const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
+				mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
+				if (L::kLoadRgb)
+					tma_load_3d(dst, map_rgb, bar_full + 8 * stage, x, (int)(t * kTileRows), (int)frame);
+				if (L::kLoadYuv)
+					tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), map_yuv, bar_full + 8 * stage, x,
+						    (int)(t * kTileRows), (int)frame);
+				if (++stage == kStages) {
+					stage = 0;
+					phase ^= 1;
 				}
 			}
 		}
-		return;
 	}
+}
 
-	// ================= consumers =================
+// One consumer warp's walk over the chunks.  R_SRC / R_VS = what THIS warp accumulates (its
+// role), N = rows of every tile it takes starting at `row0`; K_BINS / K_VS = what the kernel as
+// a whole holds in shared memory (all NWORK consumer warps meet in emit_strip / flush_vscope).
+template <class L, int R_SRC, bool R_VS, bool SURFACE, int N, int NWORK, bool K_BINS, bool K_VS>
+__device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem, uint32_t smem_base,
+					    volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty,
+					    int row0, int warp, int lane, int tid)
+{
+	constexpr int kStages = L::kStages;
+	constexpr bool kNeedP = R_SRC == SRC_RGB || (!SURFACE && (R_VS || R_SRC == SRC_YUV));
+	constexpr bool kNeedQ = SURFACE && (R_SRC == SRC_YUV || R_VS);
+	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
+	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
+	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic; // 0x4B000000 kept in a register so PRMT can take the selector as its immediate
 	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
@@ -746,15 +717,15 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 	for (;;) {
 		// the chunk id becomes readable once the chunk's first tile (or the end marker) lands
 		mbar_wait(bar_full + 8 * stage, phase);
-		const uint32_t chunk = chunk_q[qr % kQueue];
+		const uint32_t first = chunk_q[2 * (qr % kQueue)], count = chunk_q[2 * (qr % kQueue) + 1];
 		qr++;
-		if (chunk == 0xFFFFFFFFu)
+		if (count == 0u)
 			break;
-		const uint32_t first = chunk * P.chunk_items, last = min(first + P.chunk_items, P.items);
+		const uint32_t last = first + count;
 		for (uint32_t item = first; item < last; item++) {
 			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
-			if (VSCOPE && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
-				flush_vscope<NW>(P, vs, cur_frame, tid);
+			if (K_VS && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
+				flush_vscope<NWORK>(P, vs, cur_frame, tid);
 			cur_frame = frame;
 			const uint32_t x = strip * kStripPx + lane;
 			const bool lane_ok = x < P.width;
@@ -764,17 +735,17 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 			const uint32_t n_full = strip_full ? P.height / kTileRows : 0u;
 			bool skip_wait = item == first; // the chunk announcement already waited for tile 0
 			// fetch = wait for the tile, read this thread's pixels, remember which stage to hand back
-			auto fetch_tile = [&](uint32_t(&p)[RPW], uint32_t(&q)[RPW]) -> uint32_t {
+			auto fetch_tile = [&](uint32_t(&p)[N], uint32_t(&q)[N]) -> uint32_t {
 				if (!skip_wait)
 					mbar_wait(bar_full + 8 * stage, phase);
 				skip_wait = false;
 				const uint32_t *tile =
 					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes) +
-					warp * RPW * kStripPx + lane;
+					row0 * kStripPx + lane;
 #pragma unroll
-				for (int k = 0; k < RPW; k++) {
-					p[k] = L::kLoadRgb ? tile[k * kStripPx] : 0u;
-					q[k] = L::kLoadYuv ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
+				for (int k = 0; k < N; k++) {
+					p[k] = kNeedP ? tile[k * kStripPx] : 0u;
+					q[k] = kNeedQ ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
 				}
 				const uint32_t bar = bar_empty + 8 * stage;
 				if (++stage == kStages) {
@@ -788,10 +759,10 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 			// before the LDS results are in registers: under a backlog of serialised atomics the
 			// LSU can otherwise still be holding those reads when the TMA refill lands (seen as
 			// rare wrong-bin pixels on smooth content; profiles/ubench_r01.md, "WAR on the ring").
-			auto release_tile = [&](uint32_t bar, const uint32_t(&p)[RPW], const uint32_t(&q)[RPW]) {
+			auto release_tile = [&](uint32_t bar, const uint32_t(&p)[N], const uint32_t(&q)[N]) {
 				uint32_t dep = 0;
 #pragma unroll
-				for (int k = 0; k < RPW; k++)
+				for (int k = 0; k < N; k++)
 					dep |= p[k] | q[k];
 				__syncwarp();
 				if (lane == 0)
@@ -801,50 +772,133 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 			if (n_full > 0) {
 				// software pipeline over the interior tiles: atomics of tile t next to the
 				// arithmetic of tile t+1 (two Prep register sets, ping-pong)
-				uint32_t p[RPW], q[RPW];
-				Prep<RPW> A, B;
+				uint32_t p[N], q[N];
+				Prep<N> A, B;
 				uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
-				prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, A);
+				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 				for (t = 1; t + 1 < n_full; t += 2) {
 					bar = fetch_tile(p, q);
-					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
 					release_tile(bar, p, q);
-					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, B);
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
 					bar = fetch_tile(p, q);
-					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, B);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
 					release_tile(bar, p, q);
-					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, A);
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 				}
 				if (t < n_full) {
 					bar = fetch_tile(p, q);
-					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
 					release_tile(bar, p, q);
-					prepare_tile<SRC, VSCOPE, SURFACE, RPW>(tc, coef, p, q, B);
-					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, B);
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
 				} else {
-					commit_tile<SRC, VSCOPE, SURFACE, RPW>(tc, A);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
 				}
 				t = n_full;
 			}
 			for (; t < tiles; t++) {
-				// edge tiles (last rows, last strip) and partial channel masks: generic body
-				uint32_t p[RPW], q[RPW];
-				bool ok[RPW];
+				// edge tiles (last rows, last strip): generic body with per-pixel validity
+				uint32_t p[N], q[N];
+				bool ok[N];
 				const uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
-				const uint32_t y0 = t * kTileRows + warp * RPW;
+				const uint32_t y0 = t * kTileRows + row0;
 #pragma unroll
-				for (int k = 0; k < RPW; k++)
+				for (int k = 0; k < N; k++)
 					ok[k] = lane_ok && (y0 + k < P.height);
-				process_tile<SRC, VSCOPE, SURFACE, false, RPW>(tc, coef, p, q, ok);
+				process_tile<R_SRC, R_VS, SURFACE, false, N>(tc, coef, p, q, ok);
 			}
-			if (SRC != SRC_NONE)
-				emit_strip<NW>(P, wave0, frame, x, lane_ok, warp, lane);
+			if (K_BINS)
+				emit_strip<NWORK>(P, wave0, frame, x, lane_ok, warp, lane);
 		}
 	}
-	if (VSCOPE && cur_frame != 0xFFFFFFFFu)
-		flush_vscope<NW>(P, vs, cur_frame, tid);
+	if (K_VS && cur_frame != 0xFFFFFFFFu)
+		flush_vscope<NWORK>(P, vs, cur_frame, tid);
+}
+
+template <class L, int NWORK>
+__device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint32_t bar_empty, bool vscope, bool bins,
+					  bool worker, int tid)
+{
+	if (worker)
+		zero_bins<NWORK>(reinterpret_cast<uint32_t *>(smem + L::kVsOff),
+				 reinterpret_cast<uint32_t *>(smem + L::kWave0Off), vscope, bins, tid);
+	if (tid == 0) {
+		for (int s = 0; s < L::kStages; s++) {
+			mbar_init(bar_full + 8 * s, 1);
+			mbar_init(bar_empty + 8 * s, NWORK);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// strip kernel, TMA loader, every consumer warp does everything: 16 consumer warps take 4 rows
+// of each 64-row tile; 1 producer warp.  Used for all scope combinations except the one below.
+// ---------------------------------------------------------------------------
+template <int SRC, bool VSCOPE, bool SURFACE>
+__global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
+	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
+			       const __grid_constant__ CUtensorMap map_yuv)
+{
+	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
+	constexpr int NW = kTmaWarps, RPW = kTileRows / NW;
+	extern __shared__ __align__(128) uint8_t smem[];
+	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
+	const uint32_t smem_base = smem_u32(smem);
+	const uint32_t bar_full = smem_base + L::kBarOff;
+	const uint32_t bar_empty = bar_full + kMaxStages * 8;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool is_producer = warp == NW;
+
+	tma_setup<L, NW>(smem, bar_full, bar_empty, VSCOPE, SRC != SRC_NONE, !is_producer, tid);
+	if (is_producer) {
+		if (lane == 0)
+			tma_produce<L>(P, &map_rgb, &map_yuv, smem_base, chunk_q, bar_full, bar_empty);
+		return;
+	}
+	tma_consume<L, SRC, VSCOPE, SURFACE, RPW, NW, SRC != SRC_NONE, VSCOPE>(P, smem, smem_base, chunk_q, bar_full,
+									      bar_empty, warp * RPW, warp, lane, tid);
+}
+
+// ---------------------------------------------------------------------------
+// strip kernel, TMA loader, SPECIALISED warps for the headline combination (column bins on the
+// RGB plane + vectorscope): kSplitVsWarps warps only do transform + vectorscope, kSplitBinWarps
+// warps only do the waveform/histogram bins, both reading the same TMA tiles.  The vectorscope's
+// 128 KB of bins allow one CTA per SM, so the only way to more resident warps is a wider CTA;
+// the two roles have complementary instruction mixes (FP32 + 1 atomic vs 3 atomics per pixel).
+// ---------------------------------------------------------------------------
+template <bool SURFACE>
+__global__ void __launch_bounds__((kSplitVsWarps + kSplitBinWarps) * 32 + 32, 1)
+	scope_strip_kernel_split(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
+				 const __grid_constant__ CUtensorMap map_yuv)
+{
+	using L = SmemLayout<SRC_RGB, true, SURFACE, true>;
+	constexpr int NV = kSplitVsWarps, NB = kSplitBinWarps, NW = NV + NB;
+	constexpr int RV = kTileRows / NV, RB = kTileRows / NB;
+	extern __shared__ __align__(128) uint8_t smem[];
+	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
+	const uint32_t smem_base = smem_u32(smem);
+	const uint32_t bar_full = smem_base + L::kBarOff;
+	const uint32_t bar_empty = bar_full + kMaxStages * 8;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool is_producer = warp == NW;
+
+	tma_setup<L, NW>(smem, bar_full, bar_empty, true, true, !is_producer, tid);
+	if (is_producer) {
+		if (lane == 0)
+			tma_produce<L>(P, &map_rgb, &map_yuv, smem_base, chunk_q, bar_full, bar_empty);
+		return;
+	}
+	if (warp < NV)
+		tma_consume<L, SRC_NONE, true, SURFACE, RV, NW, true, true>(P, smem, smem_base, chunk_q, bar_full, bar_empty,
+									    warp * RV, warp, lane, tid);
+	else
+		tma_consume<L, SRC_RGB, false, SURFACE, RB, NW, true, true>(P, smem, smem_base, chunk_q, bar_full, bar_empty,
+									    (warp - NV) * RB, warp, lane, tid);
 }
 
 // ---------------------------------------------------------------------------
@@ -1013,12 +1067,13 @@ __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out
 	// index r<<16|g<<8|b is already the little-endian BGRA word b | g<<8 | r<<16
 	uint32_t magic;
 	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
-	const uint32_t ca[3] = {carrier<0>(i, magic), carrier<1>(i, magic), carrier<2>(i, magic)};
-	const uint32_t cb[3] = {carrier<0>(i + 1, magic), carrier<1>(i + 1, magic), carrier<2>(i + 1, magic)};
-	uint32_t ya[3], yb[3];
-	rgb_to_yuv_pair<true>(ca, cb, coef, ya, yb);
-	out[i] = (ya[0] & 0xFFu) | ((ya[1] & 0xFFu) << 8) | ((ya[2] & 0xFFu) << 16);
-	out[i + 1] = (yb[0] & 0xFFu) | ((yb[1] & 0xFFu) << 8) | ((yb[2] & 0xFFu) << 16);
+#pragma unroll
+	for (uint32_t j = i; j < i + 2; j++) {
+		const uint32_t bgr[3] = {carrier<0>(j, magic), carrier<1>(j, magic), carrier<2>(j, magic)};
+		uint32_t hi[3];
+		rgb_to_yuv_hi<true>(bgr, coef, hi);
+		out[j] = __byte_perm(__byte_perm(hi[0], hi[1], 0x3362), hi[2], 0x3610);
+	}
 }
 
 } // namespace scope

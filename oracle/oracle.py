@@ -100,10 +100,14 @@ class Oracle:
         self.lib.orc_rgb_to_yuv(_ptr(bgra), ls, w, h, colorspace, out.ctypes.data, w * 4)
         return out
 
-    def rgb_to_yuv_table(self, colorspace: int, strict: bool = False) -> Tuple[np.ndarray, bool]:
-        """All 2^24 colours: out[r<<16|g<<8|b] = u | y<<8 | v<<16; second value = clamp ever active."""
+    TRANSFORM_VARIANTS = {"exact": 0, "fp32_strict": 1, "fp32_contracted": 2}
+
+    def rgb_to_yuv_table(self, colorspace: int, variant: str = "exact") -> Tuple[np.ndarray, bool]:
+        """All 2^24 colours: out[r<<16|g<<8|b] = u | y<<8 | v<<16; second value = some value left
+        the UNORM range.  variant: "exact" (the pinned definition) or one of the two fp32
+        evaluations kept for comparison."""
         out = np.zeros(1 << 24, np.uint32)
-        clamp = self.lib.orc_rgb_to_yuv_table(colorspace, int(strict), out.ctypes.data)
+        clamp = self.lib.orc_rgb_to_yuv_table(colorspace, self.TRANSFORM_VARIANTS[variant], out.ctypes.data)
         return out, bool(clamp)
 
     def calc_colorspace(self, cs: int) -> int:

@@ -27,7 +27,8 @@
  *   RGB->YUV transform: PARITY UNPINNED.  In the reference it is a float pixel
  *   shader whose evaluation order, FMA contraction and float->UNORM8 rounding
  *   belong to the GPU driver; the reference holds no test or
- *   vector for it.  The definition below is the one SURVEY.md §8(c) froze.
+ *   vector for it.  The definition below is the exact (infinitely precise) value
+ *   of the shader's expression, which every fp32 evaluation approximates.
  */
 #include <math.h>
 #include <stddef.h>
@@ -45,23 +46,55 @@ struct orc_surface {
 };
 
 /* ------------------------------------------------------------------ */
-/* RGB -> YUV, pinned definition ("contracted", the one the product    */
-/* implements; DESIGN.md §3 explains the choice):                       */
-/*   xf = (float)X / 255.0f                     (correctly rounded)     */
-/*   p  = c0*rf ; p = fma(c1,gf,p) ; p = fma(c2,bf,p) ; t = p + off     */
-/*        i.e. the mul/mad/mad/add sequence a shader compiler emits for */
-/*        `c0*r + c1*g + c2*b + off` (data/common.effect:27-29,38-40)   */
-/*   q  = (uint8_t)floorf(fmaf(min(max(t,0),1), 255.0f, 0.5f))          */
-/* coefficients exactly as printed in the effect file; off = 0.5f -     */
-/* 1.0f/256.0f (U), 0 (Y), 0.5f (V).  Output bytes [U, Y, V, 255]       */
-/* (B<-z, G<-y, R<-x, A<-1).                                            */
+/* RGB -> YUV, pinned definition (the one the product implements;       */
+/* DESIGN.md §3 explains the choice): the EXACT value of the shader's   */
+/* expression (data/common.effect:27-29,38-40) on UNORM8 inputs,        */
+/* converted to UNORM8 the way a render target does (x*255 + 0.5,       */
+/* truncate):                                                           */
+/*   q = floor(c0*R + c1*G + c2*B + 255*off + 1/2)   in real arithmetic */
+/* with R,G,B the bytes, the coefficients exactly as printed in the     */
+/* effect file (six decimals), off = 1/2 - 1/256 (U), 0 (Y), 1/2 (V).   */
+/* With c' = 10^6 * c this is integer arithmetic:                       */
+/*   q = (c0'*R + c1'*G + c2'*B + K) / 10^6,                            */
+/*   K = floor(10^6 * (255*off + 1/2)) = 127003906 (U; the .25 dropped  */
+/*       by the floor can never carry), 500000 (Y), 128000000 (V).      */
+/* The value is always inside [0,255] (checked by the table function),  */
+/* so the shader's implicit [0,1] clamp never acts.                     */
+/* Output bytes [U, Y, V, 255] (B<-z, G<-y, R<-x, A<-1).                */
 /*                                                                      */
-/* "strict" variant = SURVEY.md §8(c)'s first draft (every product and  */
-/* sum rounded separately, no FMA anywhere); kept so the tests can      */
-/* report how many of the 2^24 colours the two definitions disagree on. */
+/* Two fp32 evaluations of the same expression are kept for the tests,  */
+/* which report on how many of the 2^24 colours a float pipeline        */
+/* deviates from the exact value (a few hundred per channel, by 1):     */
+/*   "strict"     xf = (float)X/255.0f; every product and sum rounded   */
+/*                separately, left to right (SURVEY.md §8(c)'s draft);   */
+/*   "contracted" p = c0*rf; p = fma(c1,gf,p); p = fma(c2,bf,p);        */
+/*                t = p + off; q = floor(fma(t,255,0.5)) - the mul/mad/  */
+/*                mad/add sequence a shader compiler emits.             */
 /* Build with -ffp-contract=off so the compiler adds no contraction of  */
 /* its own.                                                             */
 /* ------------------------------------------------------------------ */
+struct yuv_coeffs_i {
+	int32_t u[3], y[3], v[3]; /* 10^6 x coefficient, order R, G, B */
+};
+static const struct yuv_coeffs_i ki_bt601 = {
+	{-147643, -289855, +437500},
+	{+299000, +587000, +114000},
+	{+437500, -366351, -71147},
+};
+static const struct yuv_coeffs_i ki_bt709 = {
+	{-100643, -338571, +439216},
+	{+212600, +715200, +72200},
+	{+439216, -398941, -40273},
+};
+#define K_U 127003906
+#define K_Y 500000
+#define K_V 128000000
+
+static inline int32_t dot3_exact(const int32_t c[3], int r, int g, int b, int32_t k)
+{
+	return c[0] * r + c[1] * g + c[2] * b + k; /* |.| < 2^28: no overflow */
+}
+
 struct yuv_coeffs {
 	float u[3], y[3], v[3];
 };
@@ -119,13 +152,10 @@ static inline float dot3_strict(const float c[3], float r, float g, float b, flo
 
 ORC_API void orc_rgb_to_yuv_pixel(int colorspace, uint8_t r8, uint8_t g8, uint8_t b8, uint8_t out_uyv[3])
 {
-	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
-	const float r = (float)r8 / 255.0f;
-	const float g = (float)g8 / 255.0f;
-	const float b = (float)b8 / 255.0f;
-	out_uyv[0] = quantise_contracted(dot3_contracted(k->u, r, g, b, OFF_U));
-	out_uyv[1] = quantise_contracted(dot3_contracted(k->y, r, g, b, OFF_Y));
-	out_uyv[2] = quantise_contracted(dot3_contracted(k->v, r, g, b, OFF_V));
+	const struct yuv_coeffs_i *k = colorspace == 1 ? &ki_bt601 : &ki_bt709;
+	out_uyv[0] = (uint8_t)(dot3_exact(k->u, r8, g8, b8, K_U) / 1000000);
+	out_uyv[1] = (uint8_t)(dot3_exact(k->y, r8, g8, b8, K_Y) / 1000000);
+	out_uyv[2] = (uint8_t)(dot3_exact(k->v, r8, g8, b8, K_V) / 1000000);
 }
 
 /* Whole plane: BGRA in, [U,Y,V,255] out.  Alpha of the source is ignored
@@ -148,36 +178,50 @@ ORC_API void orc_rgb_to_yuv(const uint8_t *bgra, uint32_t linesize, uint32_t wid
 }
 
 /* Exhaustive helper for tests: all 2^24 (r,g,b) -> packed u | y<<8 | v<<16,
- * index = r<<16 | g<<8 | b.  strict != 0 selects the no-FMA variant.  Returns
- * 1 if the [0,1] clamp ever changed a value (it must not: the GPU kernel
- * relies on that and omits it). */
-ORC_API int orc_rgb_to_yuv_table(int colorspace, int strict, uint32_t *out /* 1<<24 entries */)
+ * index = r<<16 | g<<8 | b.  variant 0 = the pinned exact definition,
+ * 1 = fp32 "strict", 2 = fp32 "contracted".  Returns 1 if a value ever left
+ * the UNORM range (exact: S outside [0, 256e6); fp32: the [0,1] clamp changed
+ * something) - it must not: the GPU kernel relies on that. */
+ORC_API int orc_rgb_to_yuv_table(int colorspace, int variant, uint32_t *out /* 1<<24 entries */)
 {
 	const struct yuv_coeffs *k = colorspace == 1 ? &k_bt601 : &k_bt709;
-	int clamp_active = 0;
+	const struct yuv_coeffs_i *ki = colorspace == 1 ? &ki_bt601 : &ki_bt709;
+	int out_of_range = 0;
 	for (uint32_t r8 = 0; r8 < 256; r8++)
 		for (uint32_t g8 = 0; g8 < 256; g8++)
 			for (uint32_t b8 = 0; b8 < 256; b8++) {
-				const float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, b = (float)b8 / 255.0f;
-				float tu, ty, tv;
 				uint32_t qu, qy, qv;
-				if (strict) {
-					tu = dot3_strict(k->u, r, g, b, OFF_U);
-					ty = dot3_strict(k->y, r, g, b, OFF_Y);
-					tv = dot3_strict(k->v, r, g, b, OFF_V);
-					qu = quantise_strict(tu), qy = quantise_strict(ty), qv = quantise_strict(tv);
+				if (variant == 0) {
+					const int32_t su = dot3_exact(ki->u, r8, g8, b8, K_U);
+					const int32_t sy = dot3_exact(ki->y, r8, g8, b8, K_Y);
+					const int32_t sv = dot3_exact(ki->v, r8, g8, b8, K_V);
+					if (su < 0 || su >= 256000000 || sy < 0 || sy >= 256000000 || sv < 0 ||
+					    sv >= 256000000)
+						out_of_range = 1;
+					qu = (uint32_t)(su / 1000000), qy = (uint32_t)(sy / 1000000),
+					qv = (uint32_t)(sv / 1000000);
 				} else {
-					tu = dot3_contracted(k->u, r, g, b, OFF_U);
-					ty = dot3_contracted(k->y, r, g, b, OFF_Y);
-					tv = dot3_contracted(k->v, r, g, b, OFF_V);
-					qu = quantise_contracted(tu), qy = quantise_contracted(ty),
-					qv = quantise_contracted(tv);
+					const float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f,
+						    b = (float)b8 / 255.0f;
+					float tu, ty, tv;
+					if (variant == 1) {
+						tu = dot3_strict(k->u, r, g, b, OFF_U);
+						ty = dot3_strict(k->y, r, g, b, OFF_Y);
+						tv = dot3_strict(k->v, r, g, b, OFF_V);
+						qu = quantise_strict(tu), qy = quantise_strict(ty), qv = quantise_strict(tv);
+					} else {
+						tu = dot3_contracted(k->u, r, g, b, OFF_U);
+						ty = dot3_contracted(k->y, r, g, b, OFF_Y);
+						tv = dot3_contracted(k->v, r, g, b, OFF_V);
+						qu = quantise_contracted(tu), qy = quantise_contracted(ty),
+						qv = quantise_contracted(tv);
+					}
+					if (tu < 0.0f || tu > 1.0f || ty < 0.0f || ty > 1.0f || tv < 0.0f || tv > 1.0f)
+						out_of_range = 1;
 				}
-				if (tu < 0.0f || tu > 1.0f || ty < 0.0f || ty > 1.0f || tv < 0.0f || tv > 1.0f)
-					clamp_active = 1;
 				out[(r8 << 16) | (g8 << 8) | b8] = qu | (qy << 8) | (qv << 16);
 			}
-	return clamp_active;
+	return out_of_range;
 }
 
 /* src/util.c:25-41 with the OBS video-info lookup replaced by its default */

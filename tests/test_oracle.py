@@ -96,35 +96,50 @@ def test_alpha_rule_and_null_planes(oracle, pkg):
 
 
 def test_transform_facts(oracle):
-    """facts the CUDA kernel's arithmetic relies on"""
+    """facts the CUDA kernel's arithmetic relies on, and how far fp32 pipelines sit from the pin"""
     for cs in (1, 2):
-        tab, clamp = oracle.rgb_to_yuv_table(cs)
-        assert not clamp, "the [0,1] clamp must never act (the kernel omits it)"
-        strict, clamp_s = oracle.rgb_to_yuv_table(cs, strict=True)
-        assert not clamp_s
-        differ = int((tab != strict).sum())
-        assert differ < 500, differ      # contracted vs no-FMA definitions: ~2e-5 of all colours
+        tab, out_of_range = oracle.rgb_to_yuv_table(cs)
+        assert not out_of_range, "the value must stay inside the UNORM range (the kernel has no clamp)"
         u, v = tab & 0xFF, tab >> 16
         assert 15 <= u.min() and u.max() <= 239 and 16 <= v.min() and v.max() <= 240
+        for variant in ("fp32_strict", "fp32_contracted"):
+            ftab, clamp = oracle.rgb_to_yuv_table(cs, variant)
+            assert not clamp
+            for shift in (0, 8, 16):   # U, Y, V
+                a = ((tab >> shift) & 0xFF).astype(np.int32)
+                b = ((ftab >> shift) & 0xFF).astype(np.int32)
+                assert np.abs(a - b).max() <= 1
+                assert int((a != b).sum()) < 500      # < 3e-5 of all colours, each by one step
     assert oracle.calc_colorspace(0) == 2 and oracle.calc_colorspace(1) == 1 and oracle.calc_colorspace(7) == 2
 
 
-def test_div255_constants():
-    """x/255 == fma(x, k0, rn(x*k1)) for x in 0..255 with the constants scope_kernels.cuh uses"""
-    from fractions import Fraction
-    k0 = np.array([0x3B808081], np.uint32).view(np.float32)[0]
-    k1 = np.array([0xAF7EFEFF], np.uint32).view(np.float32)[0]
-
-    def rn32(fr):
-        f = np.float32(float(fr))
-        cands = [np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))]
-        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
-
-    for x in range(256):
-        ref = np.float32(x) / np.float32(255.0)
-        t = rn32(Fraction(x) * Fraction(float(k1)))
-        q = rn32(Fraction(x) * Fraction(float(k0)) + Fraction(float(t)))
-        assert q == ref, x
+def test_transform_is_the_exact_value(oracle):
+    """the pinned table == exact rational evaluation of the effect file's expression (python
+    integers, independent of the C code), and the kernel's multiply-high division is exact"""
+    from fractions import Fraction as F
+    coef = {1: (("-0.147643", "-0.289855", "0.437500"), ("0.299000", "0.587000", "0.114000"),
+                ("0.437500", "-0.366351", "-0.071147")),
+            2: (("-0.100643", "-0.338571", "0.439216"), ("0.212600", "0.715200", "0.072200"),
+                ("0.439216", "-0.398941", "-0.040273"))}
+    off = (F(1, 2) - F(1, 256), F(0), F(1, 2))
+    r, g, b = np.meshgrid(*(np.arange(256, dtype=np.int64),) * 3, indexing="ij")
+    magic = -(-2 ** 48 // 10 ** 6)
+    assert magic == 281474977                     # kDivMagic in scope_kernels.cuh
+    for cs in (1, 2):
+        tab = oracle.rgb_to_yuv_table(cs)[0].reshape(256, 256, 256).astype(np.int64)
+        for ch in range(3):
+            # scale everything by 256e6 so the U offset (1/2 - 1/256) is an integer too
+            scale = 256 * 10 ** 6
+            c = [int(F(x) * scale) for x in coef[cs][ch]]
+            k = (255 * off[ch] + F(1, 2)) * scale
+            assert k.denominator == 1
+            exact = (c[0] * r + c[1] * g + c[2] * b + int(k)) // scale
+            assert np.array_equal((tab >> (8 * ch)) & 0xFF, exact)
+            # the kernel's form: S in units of 1e-6, q = byte 2 of the high word of S * magic
+            s = (c[0] * r + c[1] * g + c[2] * b) // 256 + int(k) // 256
+            assert s.min() >= 0 and s.max() < 2 ** 28
+            hi = (s * magic) >> 32
+            assert np.array_equal(hi >> 16, exact) and (hi >> 24).max() == 0
 
 
 def test_intensity_mapping(oracle):
