@@ -116,6 +116,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 		     "r"(parity)
 		     : "memory");
 }
+// non-blocking: has the phase with this parity completed?  (acquire, like try_wait)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		     "selp.u32 %0, 1, 0, p;\n"
+		     "}"
+		     : "=r"(ok)
+		     : "r"(bar), "r"(parity)
+		     : "memory");
+	return ok;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z)
 {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -734,11 +748,16 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 			// tiles [0, n_full) lie completely inside the frame (uniform over the CTA)
 			const uint32_t n_full = strip_full ? P.height / kTileRows : 0u;
 			bool skip_wait = item == first; // the chunk announcement already waited for tile 0
+			// peek = ask early whether the NEXT tile has landed, so that the answer's latency
+			// hides behind arithmetic instead of stalling the warp at the top of fetch
+			uint32_t landed = 0;
+			auto peek_tile = [&]() { landed = mbar_test(bar_full + 8 * stage, phase); };
 			// fetch = wait for the tile, read this thread's pixels, remember which stage to hand back
 			auto fetch_tile = [&](uint32_t(&p)[N], uint32_t(&q)[N]) -> uint32_t {
-				if (!skip_wait)
+				if (!skip_wait && !landed)
 					mbar_wait(bar_full + 8 * stage, phase);
 				skip_wait = false;
+				landed = 0;
 				const uint32_t *tile =
 					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes) +
 					row0 * kStripPx + lane;
@@ -776,15 +795,18 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				Prep<N> A, B;
 				uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
+				peek_tile();
 				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 				for (t = 1; t + 1 < n_full; t += 2) {
 					bar = fetch_tile(p, q);
 					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
 					release_tile(bar, p, q);
+					peek_tile();
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
 					bar = fetch_tile(p, q);
 					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
 					release_tile(bar, p, q);
+					peek_tile();
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 				}
 				if (t < n_full) {
