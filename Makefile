@@ -30,3 +30,13 @@ clean:
 	rm -rf $(LIBDIR)
 	$(MAKE) -C oracle clean
 .PHONY: all product oracle clean
+
+# A/B builds for kernel work (tools/run_ab.sh benches every variants_tmp/*.so through SCOPE_LIB)
+VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
+variants:
+	@mkdir -p variants_tmp
+	$(VARIANT) -DSCOPE_LDSM=0 -DSCOPE_XORSWZ=0 -DSCOPE_DEFER=0 -o variants_tmp/base.so
+	$(VARIANT) -DSCOPE_GROUP_WARPS=23 -o variants_tmp/g23.so
+	$(VARIANT) -DSCOPE_GROUP_WARPS=27 -o variants_tmp/g27.so
+	$(VARIANT) -DSCOPE_GROUP_WARPS=31 -o variants_tmp/g31.so
+.PHONY: variants

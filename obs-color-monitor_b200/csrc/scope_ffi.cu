@@ -145,10 +145,27 @@ struct KernelChoice {
 	int smem = 0, threads = 0;
 };
 
+// Which TMA kernel serves the launches: the row-group kernel when the
+// library was built with SCOPE_GROUP_WARPS > 0, unless SCOPE_KERNEL=tile|group says otherwise
+// (kept for A/B runs; both kernels are always compiled in).
+bool use_group_kernel()
+{
+	const char *e = getenv("SCOPE_KERNEL");
+	if (e && !strcmp(e, "group"))
+		return true;
+	if (e && !strcmp(e, "tile"))
+		return false;
+	return SCOPE_GROUP_WARPS > 0;
+}
+
 template <int SRC, bool VS, bool SURF>
 void kernel_entry(bool tma, KernelChoice &k)
 {
-	if (tma) {
+	if (tma && use_group_kernel()) {
+		k.tma = scope_strip_kernel_tmag<SRC, VS, SURF>;
+		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
+		k.threads = kGroupWarps * 32 + 32;
+	} else if (tma) {
 		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
 		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
 		k.threads = kTmaWarps * 32 + 32;

@@ -24,6 +24,20 @@
 namespace scope {
 
 constexpr int kStripPx = 32;          // columns per strip == lanes per warp
+// Kernel features that can be switched off for A/B builds (tools/run_ab.sh builds the variants):
+//   SCOPE_LDSM    consumers read their 4 rows of a tile with ONE ldmatrix.x4 instead of four LDS.32
+//   SCOPE_XORSWZ  vectorscope bank swizzle by XOR (2 instructions) instead of add-mod-32 (4)
+#ifndef SCOPE_LDSM
+#define SCOPE_LDSM 1
+#endif
+#ifndef SCOPE_XORSWZ
+#define SCOPE_XORSWZ 1
+#endif
+//   SCOPE_DEFER   the vectorscope's overflow check of tile t is evaluated after the arithmetic of
+//                 tile t+1 instead of right behind the atomics (no wait for their return values)
+#ifndef SCOPE_DEFER
+#define SCOPE_DEFER 1
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -32,12 +46,19 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #endif
 constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile
 constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernel (kTileRows / kTmaWarps rows each)
+// SCOPE_GROUP_WARPS > 0 selects the row-group kernel (scope_strip_kernel_tmag) with that many
+// consumer warps for every TMA launch; 0 keeps the tile-synchronous kernel above
+#ifndef SCOPE_GROUP_WARPS
+#define SCOPE_GROUP_WARPS 0
+#endif
 #ifndef SCOPE_SPLIT_VS_WARPS
 #define SCOPE_SPLIT_VS_WARPS 16
 #endif
 #ifndef SCOPE_SPLIT_BIN_WARPS
 #define SCOPE_SPLIT_BIN_WARPS 8
 #endif
+constexpr int kGroupWarps = SCOPE_GROUP_WARPS > 0 ? SCOPE_GROUP_WARPS : 24; // consumer warps of the row-group kernel
+constexpr int kGroupRows = 4;                    // rows per group == rows one ldmatrix.x4 reads
 constexpr int kSplitVsWarps = SCOPE_SPLIT_VS_WARPS;   // specialised kernel: warps doing transform + vectorscope
 constexpr int kSplitBinWarps = SCOPE_SPLIT_BIN_WARPS; // specialised kernel: warps doing the column bins
 constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
@@ -148,6 +169,31 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
 	uint32_t v;
 	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
+}
+
+// N consecutive 128-byte tile rows -> one pixel per lane per row, i.e. exactly what
+// `p[k] = tile[k * 32 + lane]` reads, but with one LSU instruction per FOUR rows.
+// ldmatrix (m8n8, b16) hands thread T the 32-bit word T % 4 of the 16-byte row whose address
+// lane 8 j + T / 4 supplied, for j = 0..3.  With lane L supplying rows_addr + 16 L that is
+// the word at rows_addr + 128 j + 4 T: row j, pixel column T.  512 bytes per instruction at the
+// full 128 B/clk of the shared-memory crossbar (LDS.32 is issue-bound at half of that).
+template <int N>
+__device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t (&p)[N])
+{
+	if (N == 2) {
+		asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+			     : "=r"(p[0]), "=r"(p[1])
+			     : "r"(rows_addr + (uint32_t)(lane & 15) * 16u)
+			     : "memory");
+	} else {
+		// (callers only come here with N a multiple of 4)
+#pragma unroll
+		for (int k = 0; k + 3 < N; k += 4)
+			asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+				     : "=r"(p[k]), "=r"(p[k + 1]), "=r"(p[k + 2]), "=r"(p[k + 3])
+				     : "r"(rows_addr + (uint32_t)k * 128u + (uint32_t)lane * 16u)
+				     : "memory");
+	}
 }
 
 // ---------------------------------------------------------------------------
@@ -280,8 +326,25 @@ __device__ __forceinline__ void bins_add(uint32_t cb, uint32_t cg, uint32_t cr, 
 // is a bijection on the 15-bit word index; flush_vscope undoes it.
 __device__ __forceinline__ uint32_t vs_word(uint32_t idx)
 {
+#if SCOPE_XORSWZ
+	// bits 2..4 of U are XOR-ed with the low three bits of V: same spreading (simulated passes
+	// per warp-wide atomic: tools/vs_conflicts.py), two instructions instead of four, and still
+	// a permutation of 4-word groups for fixed V (what flush_vscope relies on)
+	return (idx ^ ((idx >> 6) & 0x1Cu)) & 0x7FFFu;
+#else
 	const uint32_t t = (idx >> 8) * 4u + idx; // low 5 bits: (U + 4 V) mod 32
 	return (idx & 0x7FE0u) | (t & 31u);
+#endif
+}
+// inverse of vs_word for a 4-aligned word index: the U of the group's first word (V = word >> 8)
+__device__ __forceinline__ uint32_t vs_unswizzle_u(uint32_t word)
+{
+	const uint32_t v7 = word >> 8;
+#if SCOPE_XORSWZ
+	return (word & 0xFFu) ^ ((v7 & 7u) << 2);
+#else
+	return (word & 0xE0u) | ((word - v7 * 4u) & 31u);
+#endif
 }
 
 struct VsAdd {
@@ -459,7 +522,7 @@ __device__ __forceinline__ void flush_vscope(const StripParams &P, uint32_t *vs,
 			// word = vs_word(U | V << 8): undo the bank swizzle (the four words of this
 			// uint4 stay four consecutive U values: the rotation is a multiple of 4)
 			const uint32_t word = i * 4;
-			const uint32_t v7 = word >> 8, u = (word & 0xE0u) | ((word - v7 * 4u) & 31u);
+			const uint32_t v7 = word >> 8, u = vs_unswizzle_u(word);
 			uint32_t *lo = acc + (255u - v7) * 256u + u; // V = v7
 			uint32_t *hi = acc + (127u - v7) * 256u + u; // V = v7 | 0x80
 #pragma unroll
@@ -598,8 +661,13 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 	}
 }
 
+// commit_issue: every shared-memory atomic of the tile.  The vectorscope adds return the old
+// words into `pend`; commit_resolve looks at them LATER (after the next tile's arithmetic), so
+// the warp never sits waiting for the LSU queue to hand the old values back.  Deferring the
+// check does not change the saturation argument of vs_add: a thread still has at most N
+// unchecked adds in flight, because it resolves one tile before issuing the next.
 template <int SRC, bool VSCOPE, bool SURFACE, int N>
-__device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
+__device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o, uint32_t (&pend)[N])
 {
 	if (SRC != SRC_NONE) {
 		if (o.all_counted && c.bins_mask == 7u) {
@@ -625,25 +693,42 @@ __device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
 			if (c.lane == 0)
 				vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
 		} else {
-			// N adds in flight; their old words are OR-ed and tested once for "some half
-			// already >= 0x8000" (either half: a false alarm only costs the exact re-check)
-			uint32_t old[N], any = 0;
 #pragma unroll
 			for (int k = 0; k < N; k++) {
 				const uint32_t h = o.idx[k] >> 15;
-				old[k] = atom_shared_add(vs_word(o.idx[k]) * 4u + c.vs_base, h * 0xFFFFu + 1u);
-				any |= old[k];
-			}
-			if (any & 0x80008000u) {
-#pragma unroll
-				for (int k = 0; k < N; k++) {
-					const uint32_t h = o.idx[k] >> 15;
-					if (old[k] & (h * 0x7FFF8000u + 0x8000u))
-						red_shared(vs_word(o.idx[k]) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
-				}
+				pend[k] = atom_shared_add(vs_word(o.idx[k]) * 4u + c.vs_base, h * 0xFFFFu + 1u);
 			}
 		}
 	}
+}
+
+template <int SRC, bool VSCOPE, bool SURFACE, int N>
+__device__ __forceinline__ void commit_resolve(const TileCtx &c, const Prep<N> &o, const uint32_t (&pend)[N])
+{
+	if (VSCOPE && !o.flat) {
+		// the old words are OR-ed and tested once for "some half already >= 0x8000" (either
+		// half: a false alarm only costs the exact re-check)
+		uint32_t any = 0;
+#pragma unroll
+		for (int k = 0; k < N; k++)
+			any |= pend[k];
+		if (any & 0x80008000u) {
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				const uint32_t h = o.idx[k] >> 15;
+				if (pend[k] & (h * 0x7FFF8000u + 0x8000u))
+					red_shared(vs_word(o.idx[k]) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
+			}
+		}
+	}
+}
+
+template <int SRC, bool VSCOPE, bool SURFACE, int N>
+__device__ __forceinline__ void commit_tile(const TileCtx &c, const Prep<N> &o)
+{
+	uint32_t pend[N];
+	commit_issue<SRC, VSCOPE, SURFACE, N>(c, o, pend);
+	commit_resolve<SRC, VSCOPE, SURFACE, N>(c, o, pend);
 }
 
 // ---------------------------------------------------------------------------
@@ -758,13 +843,29 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					mbar_wait(bar_full + 8 * stage, phase);
 				skip_wait = false;
 				landed = 0;
-				const uint32_t *tile =
-					reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes) +
-					row0 * kStripPx + lane;
+				if (SCOPE_LDSM && (N == 2 || N % 4 == 0)) {
+					const uint32_t rows =
+						smem_base + L::kStageOff + stage * L::kStageBytes + row0 * (kStripPx * 4);
+					if (kNeedP)
+						ldsm_rows<N>(rows, lane, p);
+					if (kNeedQ)
+						ldsm_rows<N>(rows + (L::kLoadRgb ? kTileBytes : 0), lane, q);
 #pragma unroll
-				for (int k = 0; k < N; k++) {
-					p[k] = kNeedP ? tile[k * kStripPx] : 0u;
-					q[k] = kNeedQ ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
+					for (int k = 0; k < N; k++) {
+						if (!kNeedP)
+							p[k] = 0u;
+						if (!kNeedQ)
+							q[k] = 0u;
+					}
+				} else {
+					const uint32_t *tile =
+						reinterpret_cast<const uint32_t *>(smem + L::kStageOff + stage * L::kStageBytes) +
+						row0 * kStripPx + lane;
+#pragma unroll
+					for (int k = 0; k < N; k++) {
+						p[k] = kNeedP ? tile[k * kStripPx] : 0u;
+						q[k] = kNeedQ ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
+					}
 				}
 				const uint32_t bar = bar_empty + 8 * stage;
 				if (++stage == kStages) {
@@ -790,30 +891,43 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 			uint32_t t = 0;
 			if (n_full > 0) {
 				// software pipeline over the interior tiles: atomics of tile t next to the
-				// arithmetic of tile t+1 (two Prep register sets, ping-pong)
-				uint32_t p[N], q[N];
+				// arithmetic of tile t+1 (two Prep register sets, ping-pong); the vectorscope's
+				// overflow check of tile t is looked at after that arithmetic (SCOPE_DEFER)
+				uint32_t p[N], q[N], pend[N];
 				Prep<N> A, B;
+				auto issue = [&](const Prep<N> &o) {
+					commit_issue<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+					if (!SCOPE_DEFER)
+						commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+				};
+				auto resolve = [&](const Prep<N> &o) {
+					if (SCOPE_DEFER)
+						commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+				};
 				uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
 				peek_tile();
 				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 				for (t = 1; t + 1 < n_full; t += 2) {
 					bar = fetch_tile(p, q);
-					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
+					issue(A);
 					release_tile(bar, p, q);
 					peek_tile();
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
+					resolve(A);
 					bar = fetch_tile(p, q);
-					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
+					issue(B);
 					release_tile(bar, p, q);
 					peek_tile();
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
+					resolve(B);
 				}
 				if (t < n_full) {
 					bar = fetch_tile(p, q);
-					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
+					issue(A);
 					release_tile(bar, p, q);
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
+					resolve(A);
 					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
 				} else {
 					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
@@ -840,7 +954,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 		flush_vscope<NWORK>(P, vs, cur_frame, tid);
 }
 
-template <class L, int NWORK>
+template <class L, int NWORK, int EMPTY_ARRIVALS = NWORK>
 __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint32_t bar_empty, bool vscope, bool bins,
 					  bool worker, int tid)
 {
@@ -850,7 +964,7 @@ __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint
 	if (tid == 0) {
 		for (int s = 0; s < L::kStages; s++) {
 			mbar_init(bar_full + 8 * s, 1);
-			mbar_init(bar_empty + 8 * s, NWORK);
+			mbar_init(bar_empty + 8 * s, EMPTY_ARRIVALS);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -884,6 +998,228 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
 	}
 	tma_consume<L, SRC, VSCOPE, SURFACE, RPW, NW, SRC != SRC_NONE, VSCOPE>(P, smem, smem_base, chunk_q, bar_full,
 									      bar_empty, warp * RPW, warp, lane, tid);
+}
+
+// ---------------------------------------------------------------------------
+// Row-group consumer.  In the kernel above every consumer warp owns kTileRows / NW rows of EVERY
+// tile, which ties the warp count to the tile height (16 warps x 4 rows = 64-row tiles) and makes
+// the 16 warps walk the ring in lock step.  Here the unit of work is a GROUP of 4 rows (what one
+// ldmatrix.x4 reads): the groups of a strip are numbered top to bottom, warp w takes groups
+// w, w + NW, w + 2 NW, ... whatever tile they fall in; a warp with no group in a tile just passes
+// it (see "barrier discipline" below).  The warp count is then free
+// (24 warps at <= 80 registers fill the register file), warps drift apart by up to the ring
+// depth instead of meeting at every tile, and the stage/phase of a group follow from the number
+// of tiles this CTA has consumed so far, which every warp can compute on its own.
+// ---------------------------------------------------------------------------
+template <class L, int R_SRC, bool R_VS, bool SURFACE, int NWORK, bool K_BINS, bool K_VS>
+__device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t *smem, uint32_t smem_base,
+						   volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty,
+						   int warp, int lane, int tid)
+{
+	constexpr int kStages = L::kStages;
+	constexpr int N = kGroupRows;
+	constexpr uint32_t GPT = kTileRows / kGroupRows; // groups per tile
+	static_assert(kTileRows % kGroupRows == 0, "tile height must be a multiple of the group height");
+	constexpr bool kNeedP = R_SRC == SRC_RGB || (!SURFACE && (R_VS || R_SRC == SRC_YUV));
+	constexpr bool kNeedQ = SURFACE && (R_SRC == SRC_YUV || R_VS);
+	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
+	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
+	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
+	const uint32_t groups = tiles * GPT;          // per strip, including the ones below the frame
+	const uint32_t groups_inside = P.height / N;  // groups [0, groups_inside) have all 4 rows in the frame
+	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
+	uint32_t magic;
+	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
+			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	const Coef coef = P.coef;
+	uint32_t zero;
+	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+	uint32_t tile_seq = 0;  // tiles this CTA consumed before the current strip (same in every warp)
+	// Barrier discipline.  An mbarrier wait names a phase by its parity only, so a waiter must be
+	// neither two phases ahead of the barrier nor two behind.  Every warp therefore visits EVERY
+	// tile in order, also the tiles it has no group in: it waits for the tile ("full") and then
+	// either reads its group and releases, or simply passes - one arrival per warp per tile on the
+	// "empty" barrier either way (NWORK arrivals complete a phase).  Ahead: tile n - kStages (same
+	// stage, previous phase) was waited for before tile n is asked about.  Behind: tile n + kStages
+	// cannot be loaded before this warp has arrived for tile n, which it does after its wait.
+	static_assert(NWORK >= (int)GPT, "a warp must own at most one group per tile");
+	uint32_t next_tile = 0; // first tile this warp has not finished (read + released, or passed)
+	uint32_t waited = 0;    // tiles [0, waited) have been waited for; next_tile <= waited <= next_tile + 1
+	uint32_t landed = 0;    // early answer of mbar_test for tile `waited`
+	auto ensure_waited = [&](uint32_t m) {
+		if (waited <= m) { // (then waited == m: tiles are waited for strictly in order)
+			if (!landed)
+				mbar_wait(bar_full + 8 * (m % kStages), (m / kStages) & 1u);
+			landed = 0;
+			waited = m + 1;
+		}
+	};
+	// finish every tile before n without reading it, then wait for tile n
+	auto advance_to = [&](uint32_t n) {
+		while (next_tile < n) {
+			ensure_waited(next_tile);
+			if (lane == 0)
+				mbar_arrive(bar_empty + 8 * (next_tile % kStages));
+			next_tile++;
+		}
+		ensure_waited(n);
+	};
+	// ask early whether the next tile has landed, so the answer's latency hides behind arithmetic
+	auto peek = [&]() {
+		if (waited == next_tile)
+			landed = mbar_test(bar_full + 8 * (waited % kStages), (waited / kStages) & 1u);
+	};
+	uint32_t qr = 0;
+	uint32_t cur_frame = 0xFFFFFFFFu;
+
+	for (;;) {
+		// the chunk id becomes readable once the chunk's first tile (or the end marker) lands
+		advance_to(tile_seq);
+		const uint32_t first = chunk_q[2 * (qr % kQueue)], count = chunk_q[2 * (qr % kQueue) + 1];
+		qr++;
+		if (count == 0u)
+			break;
+		const uint32_t last = first + count;
+		for (uint32_t item = first; item < last; item++) {
+			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
+			if (K_VS && frame != cur_frame && cur_frame != 0xFFFFFFFFu)
+				flush_vscope<NWORK>(P, vs, cur_frame, tid);
+			cur_frame = frame;
+			const uint32_t x = strip * kStripPx + lane;
+			const bool lane_ok = x < P.width;
+			const bool strip_full = strip * kStripPx + kStripPx <= P.width;
+			const uint32_t n_fast = strip_full ? groups_inside : 0u; // groups with no validity logic
+
+			// wait for group g's tile, read this thread's 4 pixels; returns the barrier to release
+			auto fetch = [&](uint32_t g, uint32_t(&p)[N], uint32_t(&q)[N]) -> uint32_t {
+				const uint32_t n = tile_seq + g / GPT, stage = n % kStages;
+				advance_to(n);
+				next_tile = n + 1; // (the caller releases right after)
+				const uint32_t rows = smem_base + L::kStageOff + stage * L::kStageBytes +
+						      (g % GPT) * (N * kStripPx * 4);
+				if (kNeedP)
+					ldsm_rows<N>(rows, lane, p);
+				if (kNeedQ)
+					ldsm_rows<N>(rows + (L::kLoadRgb ? kTileBytes : 0), lane, q);
+#pragma unroll
+				for (int k = 0; k < N; k++) {
+					if (!kNeedP)
+						p[k] = 0u;
+					if (!kNeedQ)
+						q[k] = 0u;
+				}
+				return bar_empty + 8 * stage;
+			};
+			// hand the group back (data-dependent on the loaded pixels: see release_tile above)
+			auto release = [&](uint32_t bar, const uint32_t(&p)[N], const uint32_t(&q)[N]) {
+				uint32_t dep = 0;
+#pragma unroll
+				for (int k = 0; k < N; k++)
+					dep |= p[k] | q[k];
+				__syncwarp();
+				if (lane == 0)
+					mbar_arrive(bar + (dep & zero));
+			};
+
+			uint32_t g = warp;
+			if (g < n_fast) {
+				// software pipeline over this warp's interior groups (ping-pong A / B)
+				uint32_t p[N], q[N], pend[N];
+				Prep<N> A, B;
+				auto issue = [&](const Prep<N> &o) {
+					commit_issue<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+					if (!SCOPE_DEFER)
+						commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+				};
+				auto resolve = [&](const Prep<N> &o) {
+					if (SCOPE_DEFER)
+						commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, o, pend);
+				};
+				uint32_t bar = fetch(g, p, q);
+				release(bar, p, q);
+				peek();
+				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
+				g += NWORK;
+				for (; g + NWORK < n_fast; g += 2 * NWORK) {
+					bar = fetch(g, p, q);
+					issue(A);
+					release(bar, p, q);
+					peek();
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
+					resolve(A);
+					bar = fetch(g + NWORK, p, q);
+					issue(B);
+					release(bar, p, q);
+					peek();
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
+					resolve(B);
+				}
+				if (g < n_fast) {
+					bar = fetch(g, p, q);
+					issue(A);
+					release(bar, p, q);
+					peek();
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, B);
+					resolve(A);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, B);
+					g += NWORK;
+				} else {
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, A);
+				}
+			}
+			for (; g < groups; g += NWORK) {
+				// edge groups (last rows, last strip, rows below the frame): per-pixel validity
+				uint32_t p[N], q[N];
+				bool ok[N];
+				const uint32_t bar = fetch(g, p, q);
+				release(bar, p, q);
+				const uint32_t y0 = g * N;
+#pragma unroll
+				for (int k = 0; k < N; k++)
+					ok[k] = lane_ok && (y0 + k < P.height);
+				if (y0 < P.height)
+					process_tile<R_SRC, R_VS, SURFACE, false, N>(tc, coef, p, q, ok);
+			}
+			// pass the strip's remaining tiles (the ones after this warp's last group)
+			tile_seq += tiles;
+			while (next_tile < tile_seq) {
+				ensure_waited(next_tile);
+				if (lane == 0)
+					mbar_arrive(bar_empty + 8 * (next_tile % kStages));
+				next_tile++;
+			}
+			if (K_BINS)
+				emit_strip<NWORK>(P, wave0, frame, x, lane_ok, warp, lane);
+		}
+	}
+	if (K_VS && cur_frame != 0xFFFFFFFFu)
+		flush_vscope<NWORK>(P, vs, cur_frame, tid);
+}
+
+template <int SRC, bool VSCOPE, bool SURFACE>
+__global__ void __launch_bounds__(kGroupWarps * 32 + 32, 1)
+	scope_strip_kernel_tmag(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
+				const __grid_constant__ CUtensorMap map_yuv)
+{
+	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
+	constexpr int NW = kGroupWarps;
+	extern __shared__ __align__(128) uint8_t smem[];
+	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
+	const uint32_t smem_base = smem_u32(smem);
+	const uint32_t bar_full = smem_base + L::kBarOff;
+	const uint32_t bar_empty = bar_full + kMaxStages * 8;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool is_producer = warp == NW;
+
+	tma_setup<L, NW>(smem, bar_full, bar_empty, VSCOPE, SRC != SRC_NONE, !is_producer, tid);
+	if (is_producer) {
+		if (lane == 0)
+			tma_produce<L>(P, &map_rgb, &map_yuv, smem_base, chunk_q, bar_full, bar_empty);
+		return;
+	}
+	tma_consume_groups<L, SRC, VSCOPE, SURFACE, NW, SRC != SRC_NONE, VSCOPE>(P, smem, smem_base, chunk_q, bar_full,
+										  bar_empty, warp, lane, tid);
 }
 
 // ---------------------------------------------------------------------------
