@@ -35,8 +35,9 @@ clean:
 VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
 variants:
 	@mkdir -p variants_tmp
-	$(VARIANT) -DSCOPE_LDSM=0 -DSCOPE_XORSWZ=0 -DSCOPE_DEFER=0 -o variants_tmp/base.so
-	$(VARIANT) -DSCOPE_GROUP_WARPS=23 -o variants_tmp/g23.so
-	$(VARIANT) -DSCOPE_GROUP_WARPS=27 -o variants_tmp/g27.so
-	$(VARIANT) -DSCOPE_GROUP_WARPS=31 -o variants_tmp/g31.so
+	$(VARIANT) -DSCOPE_LDSM=0 -DSCOPE_XORSWZ=0 -DSCOPE_DEFER=0 -DSCOPE_FADDR=0 -DSCOPE_FAST_EMIT=0 -o variants_tmp/base.so
+	$(VARIANT) -DSCOPE_FADDR=0 -o variants_tmp/nofaddr.so
+	$(VARIANT) -DSCOPE_FAST_EMIT=0 -o variants_tmp/noemit.so
+	$(VARIANT) -DSCOPE_MAX_CHUNK=20 -o variants_tmp/chunk20.so
+	$(VARIANT) -DSCOPE_DEFER=0 -o variants_tmp/nodefer.so
 .PHONY: variants

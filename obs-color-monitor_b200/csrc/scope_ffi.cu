@@ -98,8 +98,8 @@ int fail(scope_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess
 
 // 10^6 x the coefficients printed in data/common.effect:27-29 (BT.601) and :38-40 (BT.709), as
 // integers, order R, G, B; K = floor(10^6 * (255 * off + 1/2)) with off = 1/2 - 1/256 (U), 0 (Y),
-// 1/2 (V).  The kernel multiplies carriers (0x4B000000 + byte), so the bias they add is taken out
-// of K here (mod 2^32).
+// 1/2 (V).  The kernel multiplies carriers (kCarrierBias + byte), so the bias they add is taken out
+// of K here (mod 2^32; the bias is 0 in SCOPE_FADDR builds).
 Coef coef_for(int colorspace)
 {
 	static const int32_t k601[3][3] = {{-147643, -289855, +437500}, {+299000, +587000, +114000},
@@ -117,7 +117,7 @@ Coef coef_for(int colorspace)
 			rows[ch][i] = (uint32_t)m[ch][i];
 			sum += (uint32_t)m[ch][i];
 		}
-		*adds[ch] = k_add[ch] - sum * 0x4B000000u;
+		*adds[ch] = k_add[ch] - sum * kCarrierBias;
 	}
 	return c;
 }

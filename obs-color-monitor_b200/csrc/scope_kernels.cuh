@@ -38,6 +38,15 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_DEFER
 #define SCOPE_DEFER 1
 #endif
+//   SCOPE_FADDR   bin addresses and the vectorscope addend are formed by FFMA on denormals (the
+//                 FMA-lite pipe) instead of IMAD / LEA (the half-rate FMA-heavy and ALU pipes)
+#ifndef SCOPE_FADDR
+#define SCOPE_FADDR 1
+#endif
+//   SCOPE_FAST_EMIT  end-of-strip write-out with 24 instead of 62 instructions per level
+#ifndef SCOPE_FAST_EMIT
+#define SCOPE_FAST_EMIT 1
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -64,7 +73,10 @@ constexpr int kSplitBinWarps = SCOPE_SPLIT_BIN_WARPS; // specialised kernel: war
 constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
 constexpr int kMaxStages = 8;              // upper bound of the ring depth (barrier storage)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
-constexpr int kMaxChunkItems = 10;    // upper bound of strips per dynamically claimed chunk
+#ifndef SCOPE_MAX_CHUNK
+#define SCOPE_MAX_CHUNK 10
+#endif
+constexpr int kMaxChunkItems = SCOPE_MAX_CHUNK; // upper bound of strips per dynamically claimed chunk
 constexpr int kQueue = 4;             // chunk mailbox entries {first strip, count} (producer is < kQueue chunks ahead)
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
@@ -204,6 +216,21 @@ __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t
 //   * (carrier << 7) + (base - 0x80000000) == base + 128*b   (0x4B000000 << 7 = 0x80000000
 //     mod 2^32), so a waveform bin address is ONE multiply-add away from a carrier.
 // ---------------------------------------------------------------------------
+// With SCOPE_FADDR the bias is 0: a byte b travels as the plain integer b, which read as a float
+// is the DENORMAL b * 2^-149.  FFMA without .ftz is exact on denormals, so
+//   fma(b, 128.0, base) = (128 b + base) * 2^-149, whose bit pattern is the integer 128 b + base:
+// the bin address comes out of the FMA pipe (full rate, shared with nothing else in this kernel)
+// instead of the half-rate FMA-heavy (IMAD) or ALU (LEA) pipes that bound the inner loop.
+constexpr uint32_t kCarrierBias = SCOPE_FADDR ? 0u : 0x4B000000u;
+
+// a * b + c on the bit patterns of small non-negative integers (all < 2^23), b a float constant
+__device__ __forceinline__ uint32_t fma_bits(uint32_t a, float b, uint32_t c)
+{
+	float d;
+	asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(__uint_as_float(a)), "f"(b), "f"(__uint_as_float(c)));
+	return __float_as_uint(d);
+}
+
 template <int K>
 __device__ __forceinline__ uint32_t carrier(uint32_t pixel, uint32_t magic)
 {
@@ -301,12 +328,21 @@ template <bool DO_B, bool DO_G, bool DO_R>
 __device__ __forceinline__ void bins_add(uint32_t cb, uint32_t cg, uint32_t cr, uint32_t wb0, uint32_t wb1,
 					 uint32_t one)
 {
+#if SCOPE_FADDR
+	if (DO_B)
+		red_shared(fma_bits(cb, 128.0f, wb0), one);
+	if (DO_G)
+		red_shared(fma_bits(cg, 128.0f, wb0), one << 16);
+	if (DO_R)
+		red_shared(fma_bits(cr, 128.0f, wb1), one);
+#else
 	if (DO_B)
 		red_shared(cb * 128u + wb0, one);
 	if (DO_G)
 		red_shared(cg * 128u + wb0, one << 16);
 	if (DO_R)
 		red_shared(cr * 128u + wb1, one);
+#endif
 }
 
 // Vectorscope bins in shared memory are indexed by idx = U | V << 8 (NOT yet flipped to the
@@ -347,6 +383,24 @@ __device__ __forceinline__ uint32_t vs_unswizzle_u(uint32_t word)
 #endif
 }
 
+// byte address of a bin's word, and the addend that puts k into the bin's half (h = idx >> 15)
+__device__ __forceinline__ uint32_t vs_addr(uint32_t vs_base, uint32_t idx)
+{
+#if SCOPE_FADDR
+	return fma_bits(vs_word(idx), 4.0f, vs_base);
+#else
+	return vs_word(idx) * 4u + vs_base;
+#endif
+}
+__device__ __forceinline__ uint32_t vs_one(uint32_t idx)
+{
+#if SCOPE_FADDR
+	return fma_bits(idx >> 15, 65535.0f, 1u);
+#else
+	return (idx >> 15) * 0xFFFFu + 1u;
+#endif
+}
+
 struct VsAdd {
 	uint32_t addr, add, sat;
 };
@@ -354,7 +408,7 @@ __device__ __forceinline__ VsAdd vs_add(uint32_t vs_base, uint32_t idx, uint32_t
 {
 	VsAdd r;
 	const uint32_t h = idx >> 15;            // 0: lower half (V < 128), 1: upper half
-	r.addr = vs_word(idx) * 4u + vs_base;
+	r.addr = vs_addr(vs_base, idx);
 	r.add = h * (k * 0xFFFFu) + k;           // k << 16 for the upper half, k for the lower
 	const uint32_t old = atom_shared_add(r.addr, r.add);
 	r.sat = old & (h * 0x7FFF8000u + 0x8000u);
@@ -515,24 +569,35 @@ __device__ __forceinline__ void flush_vscope(const StripParams &P, uint32_t *vs,
 {
 	workers_bar<NW>();
 	uint32_t *acc = P.vscope_acc + (size_t)frame * P.vscope_stride;
-	for (int i = tid; i < kVsWords / 4; i += NW * 32) {
-		uint4 w = reinterpret_cast<uint4 *>(vs)[i];
-		if ((w.x | w.y | w.z | w.w) != 0u) {
-			const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-			// word = vs_word(U | V << 8): undo the bank swizzle (the four words of this
-			// uint4 stay four consecutive U values: the rotation is a multiple of 4)
-			const uint32_t word = i * 4;
-			const uint32_t v7 = word >> 8, u = vs_unswizzle_u(word);
-			uint32_t *lo = acc + (255u - v7) * 256u + u; // V = v7
-			uint32_t *hi = acc + (127u - v7) * 256u + u; // V = v7 | 0x80
+	constexpr int kStep = NW * 32, kBatch = 4; // kBatch loads in flight per thread
+	for (int i0 = tid; i0 < kVsWords / 4; i0 += kBatch * kStep) {
+		uint4 wv[kBatch];
 #pragma unroll
-			for (int j = 0; j < 4; j++) {
-				if (ww[j] & 0xFFFFu)
-					atomicAdd(lo + j, ww[j] & 0xFFFFu);
-				if (ww[j] >> 16)
-					atomicAdd(hi + j, ww[j] >> 16);
+		for (int b = 0; b < kBatch; b++) {
+			const int i = i0 + b * kStep;
+			wv[b] = i < kVsWords / 4 ? reinterpret_cast<uint4 *>(vs)[i] : make_uint4(0, 0, 0, 0);
+		}
+#pragma unroll
+		for (int b = 0; b < kBatch; b++) {
+			const int i = i0 + b * kStep;
+			const uint4 w = wv[b];
+			if ((w.x | w.y | w.z | w.w) != 0u) {
+				const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+				// word = vs_word(U | V << 8): undo the bank swizzle (the four words of this
+				// uint4 stay four consecutive U values: the swizzle permutes groups of 4)
+				const uint32_t word = i * 4;
+				const uint32_t v7 = word >> 8, u = vs_unswizzle_u(word);
+				uint32_t *lo = acc + (255u - v7) * 256u + u; // V = v7
+				uint32_t *hi = acc + (127u - v7) * 256u + u; // V = v7 | 0x80
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					if (ww[j] & 0xFFFFu)
+						atomicAdd(lo + j, ww[j] & 0xFFFFu);
+					if (ww[j] >> 16)
+						atomicAdd(hi + j, ww[j] >> 16);
+				}
+				reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
 			}
-			reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
 		}
 	}
 	workers_bar<NW>();
@@ -547,6 +612,54 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 	workers_bar<NW>();
 	uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
 	const uint32_t xo = P.x_offset + x;
+	if (SCOPE_FAST_EMIT && NW >= 8 && !P.partial && P.wave_mask == 7u && (P.hist_mask == 7u || P.hist_mask == 0u)) {
+		// The common case (all three channels to the waveform, all or none to the histogram),
+		// without per-level tests of launch-uniform flags.  Levels whose 32 columns are all empty
+		// (most levels, for picture content) only get their zero row written.  The warp's column
+		// sums stay in registers - lane i keeps those of the warp's i-th level - and go out as one
+		// atomic per channel per warp at the end instead of three predicated ones per level.
+		uint32_t *dst = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride) + xo;
+		const bool do_hist = P.hist_mask != 0u;
+		uint32_t keep_b = 0, keep_g = 0, keep_r = 0;
+		int i = 0;
+#pragma unroll 4
+		for (int v = warp; v < 256; v += NW, i++) {
+			const uint32_t w0 = wave0[v * 32 + lane];
+			const uint32_t w1 = wave0[kWaveWords + v * 32 + lane];
+			uint32_t *row = dst + (size_t)(255 - v) * P.out_width;
+			if (!__any_sync(0xFFFFFFFFu, (w0 | w1) != 0u)) {
+				if (lane_ok)
+					*row = 0u;
+				continue;
+			}
+			wave0[v * 32 + lane] = 0;
+			wave0[kWaveWords + v * 32 + lane] = 0;
+			const uint32_t cb = w0 & 0xFFFFu, cg = w0 >> 16, cr = w1 & 0xFFFFu;
+			if (do_hist) {
+				const uint32_t sb = __reduce_add_sync(0xFFFFFFFFu, cb);
+				const uint32_t sg = __reduce_add_sync(0xFFFFFFFFu, cg);
+				const uint32_t sr = __reduce_add_sync(0xFFFFFFFFu, cr);
+				if (lane == i) {
+					keep_b = sb;
+					keep_g = sg;
+					keep_r = sr;
+				}
+			}
+			if (lane_ok)
+				*row = min(cb, 255u) | (min(cg, 255u) << 8) | (min(cr, 255u) << 16);
+		}
+		const int v = warp + lane * NW; // the level whose sums this lane kept
+		if (do_hist && v < 256) {
+			if (keep_r)
+				atomicAdd(hist + v * 4 + 0, keep_r);
+			if (keep_g)
+				atomicAdd(hist + v * 4 + 1, keep_g);
+			if (keep_b)
+				atomicAdd(hist + v * 4 + 2, keep_b);
+		}
+		workers_bar<NW>();
+		return;
+	}
 	for (int v = warp; v < 256; v += NW) {
 		const uint32_t w0 = wave0[v * 32 + lane];
 		const uint32_t w1 = wave0[kWaveWords + v * 32 + lane];
@@ -695,8 +808,7 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 		} else {
 #pragma unroll
 			for (int k = 0; k < N; k++) {
-				const uint32_t h = o.idx[k] >> 15;
-				pend[k] = atom_shared_add(vs_word(o.idx[k]) * 4u + c.vs_base, h * 0xFFFFu + 1u);
+				pend[k] = atom_shared_add(vs_addr(c.vs_base, o.idx[k]), vs_one(o.idx[k]));
 			}
 		}
 	}
@@ -717,7 +829,7 @@ __device__ __forceinline__ void commit_resolve(const TileCtx &c, const Prep<N> &
 			for (int k = 0; k < N; k++) {
 				const uint32_t h = o.idx[k] >> 15;
 				if (pend[k] & (h * 0x7FFF8000u + 0x8000u))
-					red_shared(vs_word(o.idx[k]) * 4u + c.vs_base, 0u - (h * 0xFFFFu + 1u));
+					red_shared(vs_addr(c.vs_base, o.idx[k]), 0u - vs_one(o.idx[k]));
 			}
 		}
 	}
@@ -804,9 +916,9 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic; // 0x4B000000 kept in a register so PRMT can take the selector as its immediate
-	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
-	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
-			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
+			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
 	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
 	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
@@ -941,10 +1053,17 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				const uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
 				const uint32_t y0 = t * kTileRows + row0;
+				if (strip_full && y0 + N <= P.height) {
+					// this warp's rows of the partial tile are all inside the frame
+					Prep<N> E;
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, E);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, E);
+				} else if (y0 < P.height) {
 #pragma unroll
-				for (int k = 0; k < N; k++)
-					ok[k] = lane_ok && (y0 + k < P.height);
-				process_tile<R_SRC, R_VS, SURFACE, false, N>(tc, coef, p, q, ok);
+					for (int k = 0; k < N; k++)
+						ok[k] = lane_ok && (y0 + k < P.height);
+					process_tile<R_SRC, R_VS, SURFACE, false, N>(tc, coef, p, q, ok);
+				}
 			}
 			if (K_BINS)
 				emit_strip<NWORK>(P, wave0, frame, x, lane_ok, warp, lane);
@@ -1029,9 +1148,9 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 	const uint32_t groups_inside = P.height / N;  // groups [0, groups_inside) have all 4 rows in the frame
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic;
-	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
-	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
-			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
+			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
 	uint32_t zero;
 	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
@@ -1285,9 +1404,9 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic;
-	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
-	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - 0x80000000u,
-			 wave_lane_addr - 0x80000000u + kWaveWords * 4, magic, P.bins_mask, lane};
+	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
+			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
 	uint32_t cur_frame = 0xFFFFFFFFu;
 
@@ -1424,7 +1543,7 @@ __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out
 	const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 2;
 	// index r<<16|g<<8|b is already the little-endian BGRA word b | g<<8 | r<<16
 	uint32_t magic;
-	asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
 #pragma unroll
 	for (uint32_t j = i; j < i + 2; j++) {
 		const uint32_t bgr[3] = {carrier<0>(j, magic), carrier<1>(j, magic), carrier<2>(j, magic)};
