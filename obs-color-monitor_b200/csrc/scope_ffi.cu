@@ -221,9 +221,11 @@ int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x
 							  : (cuuint64_t)(((size_t)linesize * height + 15) & ~(size_t)15)};
 	cuuint32_t box[3] = {(cuuint32_t)kStripPx, (cuuint32_t)kTileRows, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
+	const char *l2 = getenv("SCOPE_TMA_L2"); // experiment: SCOPE_TMA_L2=0 turns the L2 promotion off
 	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base16, dims, strides, box, estr,
 				 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-				 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+				 l2 && l2[0] == '0' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+				 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		char buf[128];
 		snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -292,12 +294,23 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	P.vscope_stride = rq.vs_stride;
 	P.coef = coef_for(rq.colorspace);
 
-	// Loader choice.  TMA can describe the planes only if base pointers, pitch and frame
-	// stride are multiples of 16 bytes; everything else takes the direct loader.
+	// Loader choice.  TMA can describe the planes if base pointers, pitch and frame stride are
+	// multiples of 16 bytes; everything else (e.g. an ROI crop at an odd column, common.c:272-282)
+	// takes the direct loader.  A map that starts at the pointer rounded down to 16 bytes with
+	// boxes starting 0..3 pixels further right (tma_x0_*) would cover those crops too, but:
 	// SCOPE_LOADER=tma|ldg overrides the default (see DESIGN.md section 4.4 for the measurements).
+	// MEASURED (round 1, gpurun_out/final2/x0_sanitizer.log): sm_100a traps with "Illegal
+	// instruction" inside cp.async.bulk.tensor when the box's first pixel is not 16-byte aligned
+	// in global memory (compute-sanitizer points at tma_load_3d), with or without L2 promotion.
+	// So the x-offset path stays an experiment (SCOPE_TMA_X0=1) and planes whose base is only
+	// pixel-aligned go to the direct loader.
+	const char *x0_env = getenv("SCOPE_TMA_X0");
+	const bool allow_x0 = x0_env && x0_env[0] == '1';
+	P.tma_x0_rgb = (uint32_t)(((uintptr_t)rq.rgb & 15u) / 4u);
+	P.tma_x0_yuv = (uint32_t)(((uintptr_t)rq.yuv & 15u) / 4u);
 	const bool tma_ok = ctx->encode != nullptr && (rq.linesize % 16u) == 0 &&
 			    (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0) &&
-			    (!need_rgb || ((uintptr_t)rq.rgb & 15u) == 0) && (!need_yuv || ((uintptr_t)rq.yuv & 15u) == 0);
+			    (allow_x0 || ((!need_rgb || P.tma_x0_rgb == 0) && (!need_yuv || P.tma_x0_yuv == 0)));
 	const char *loader = getenv("SCOPE_LOADER");
 	bool use_tma = tma_ok && ctx->default_tma;
 	if (loader && !strcmp(loader, "tma"))
@@ -310,12 +323,14 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	memset(&map_yuv, 0, sizeof map_yuv);
 	if (use_tma) {
 		if (need_rgb) {
-			int r = make_map(ctx, &map_rgb, rq.rgb, rq.width, rq.linesize, rq.height, rq.n_frames, rq.frame_stride);
+			int r = make_map(ctx, &map_rgb, rq.rgb - 4u * P.tma_x0_rgb, rq.width + P.tma_x0_rgb, rq.linesize,
+					 rq.height, rq.n_frames, rq.frame_stride);
 			if (r)
 				return r;
 		}
 		if (need_yuv) {
-			int r = make_map(ctx, &map_yuv, rq.yuv, rq.width, rq.linesize, rq.height, rq.n_frames, rq.frame_stride);
+			int r = make_map(ctx, &map_yuv, rq.yuv - 4u * P.tma_x0_yuv, rq.width + P.tma_x0_yuv, rq.linesize,
+					 rq.height, rq.n_frames, rq.frame_stride);
 			if (r)
 				return r;
 		}

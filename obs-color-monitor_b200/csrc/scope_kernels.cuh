@@ -107,6 +107,8 @@ struct StripParams {
 	uint32_t x_offset;        // first output column (tile-sharded frames)
 	uint32_t out_width;       // row length of the waveform output in pixels
 	uint32_t partial;         // 1: add u16 pairs into wave_pairs instead of writing u8
+	uint32_t tma_x0_rgb, tma_x0_yuv; // TMA kernels: pixel column of the plane's first pixel inside its tensor map
+	                                 // (the map starts at the plane pointer rounded down to 16 bytes)
 	uint32_t *chunk_counter;  // global work counter of this launch (zeroed by the host)
 	uint32_t *hist;           // [n][1024] u32, zeroed
 	uint8_t *wave;            // [n][256][out_width][4]
@@ -887,10 +889,11 @@ __device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensor
 				const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
 				mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
 				if (L::kLoadRgb)
-					tma_load_3d(dst, map_rgb, bar_full + 8 * stage, x, (int)(t * kTileRows), (int)frame);
+					tma_load_3d(dst, map_rgb, bar_full + 8 * stage, x + (int)P.tma_x0_rgb, (int)(t * kTileRows),
+						    (int)frame);
 				if (L::kLoadYuv)
-					tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), map_yuv, bar_full + 8 * stage, x,
-						    (int)(t * kTileRows), (int)frame);
+					tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), map_yuv, bar_full + 8 * stage,
+						    x + (int)P.tma_x0_yuv, (int)(t * kTileRows), (int)frame);
 				if (++stage == kStages) {
 					stage = 0;
 					phase ^= 1;
@@ -1094,8 +1097,13 @@ __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint
 // strip kernel, TMA loader, every consumer warp does everything: 16 consumer warps take 4 rows
 // of each 64-row tile; 1 producer warp.  Used for all scope combinations except the one below.
 // ---------------------------------------------------------------------------
+// Without the vectorscope's 128 KB of bins two CTAs fit in an SM's shared memory; the register
+// budget is then 56 per thread (34 warps), which the kernels without a colour transform meet.
 template <int SRC, bool VSCOPE, bool SURFACE>
-__global__ void __launch_bounds__(kTmaWarps * 32 + 32, 1)
+constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
+
+template <int SRC, bool VSCOPE, bool SURFACE>
+__global__ void __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
 	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
 			       const __grid_constant__ CUtensorMap map_yuv)
 {
