@@ -116,6 +116,7 @@ void b200_roi_surface_cb(void *data, struct cm_surface_data *surface_data);
 #define B200_CM_SURFACE_QUEUE_SIZE 3
 #define B200_CM_FLAG_CONVERT_RGB 1
 #define B200_CM_FLAG_CONVERT_YUV 2
+#define B200_CM_FLAG_ROI 8 /* crop to (x0, y0)-(x1, y1) before staging (common.h:93, common.c:272-282) */
 
 struct b200_cm_queue_item {
 	uint8_t *staged;          /* host copy of the surface: RGB rows then YUV rows (common.c:358-364) */
@@ -143,6 +144,9 @@ struct b200_cm_source {
 	int colorspace;
 	/* statistics for tests */
 	volatile unsigned long frames_dropped, frames_processed;
+	/* ROI rectangle in pixels of the (already scaled) target, used when B200_CM_FLAG_ROI is set
+	 * and 0 <= x0 < x1, 0 <= y0 < y1 (common.h:61, common.c:272-282); written by b200_cm_set_roi */
+	int x0, x1, y0, y1;
 };
 
 void b200_cm_create(struct b200_cm_source *src);
@@ -155,6 +159,11 @@ void b200_cm_tick(struct b200_cm_source *src);
  * frame was already rendered in this tick (common.c:225-227). */
 bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const uint8_t *yuv, uint32_t linesize,
 			   uint32_t width, uint32_t height);
+/* roi_send_range (roi.c:478-500): clamp the requested rectangle to the target (negative or
+ * too large ends snap to the border) and hand it to the capture core, which then stages only
+ * that sub-rectangle: the callbacks see width = x1 - x0, height = y1 - y0 (common.c:272-291). */
+void b200_cm_set_roi(struct b200_cm_source *src, int x0in, int y0in, int x1in, int y1in, uint32_t target_width,
+		     uint32_t target_height);
 /* ROI pacing around the capture core: call b200_roi_tick then b200_roi_target_render once per frame.
  * roi_tick (roi.c:523-532) only ticks the capture core on the staging phase of the interleave;
  * roi_target_render (roi.c:266-277) only stages on that phase.  Returns what the reference returns

@@ -446,8 +446,23 @@ bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const
 		return false;
 	}
 
+	/* crop rectangle (common.c:272-282): the ROI if the flag is set and the rectangle is sane
+	 * and inside the frame, the whole frame otherwise */
+	uint32_t x = 0, y = 0, cx = width, cy = height;
+	if ((src->flags & B200_CM_FLAG_ROI) && 0 <= src->x0 && src->x0 < src->x1 && 0 <= src->y0 && src->y0 < src->y1 &&
+	    (uint32_t)src->x1 <= width && (uint32_t)src->y1 <= height) {
+		x = (uint32_t)src->x0;
+		y = (uint32_t)src->y0;
+		cx = (uint32_t)src->x1 - x;
+		cy = (uint32_t)src->y1 - y;
+	}
+	const bool whole = cx == width && cy == height;
+	/* the staged surface is cx wide (prepare_stagesurface, common.c:130-139); a whole frame keeps
+	 * the caller's pitch so that it moves with one memcpy per plane */
+	const uint32_t out_linesize = whole ? linesize : cx * 4u;
+
 	struct b200_cm_queue_item *item = &src->queue[src->i_write_queue];
-	const size_t plane = (size_t)linesize * height;
+	const size_t plane = (size_t)out_linesize * cy;
 	const size_t need = plane * ((has_rgb ? 1 : 0) + (has_yuv ? 1 : 0));
 	if (item->staged_bytes < need) {
 		free(item->staged);
@@ -457,15 +472,22 @@ bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const
 			return false;
 	}
 	uint8_t *dst = item->staged; /* "gs_stage_texture": RGB rows first, YUV rows below */
-	if (has_rgb) {
-		memcpy(dst, rgb, plane);
+	const uint8_t *planes[2] = {has_rgb ? rgb : NULL, has_yuv ? yuv : NULL};
+	for (int p = 0; p < 2; p++) {
+		if (!planes[p])
+			continue;
+		if (whole) {
+			memcpy(dst, planes[p], plane);
+		} else {
+			const uint8_t *from = planes[p] + (size_t)y * linesize + (size_t)x * 4u;
+			for (uint32_t r = 0; r < cy; r++)
+				memcpy(dst + (size_t)r * out_linesize, from + (size_t)r * linesize, out_linesize);
+		}
 		dst += plane;
 	}
-	if (has_yuv)
-		memcpy(dst, yuv, plane);
-	item->width = width;
-	item->height = height;
-	item->linesize = linesize;
+	item->width = cx;
+	item->height = cy;
+	item->linesize = out_linesize;
 	item->flags = (has_rgb ? B200_CM_FLAG_CONVERT_RGB : 0) | (has_yuv ? B200_CM_FLAG_CONVERT_YUV : 0);
 	item->colorspace = src->colorspace;
 	item->cb = src->callback;
@@ -477,6 +499,27 @@ bool b200_cm_render_target(struct b200_cm_source *src, const uint8_t *rgb, const
 	pthread_cond_broadcast(&src->pipeline_cond);
 	pthread_mutex_unlock(&src->pipeline_mutex);
 	return true;
+}
+
+void b200_cm_set_roi(struct b200_cm_source *src, int x0in, int y0in, int x1in, int y1in, uint32_t target_width,
+		     uint32_t target_height)
+{
+	/* roi.c:478-500 */
+	const int w = (int)target_width, h = (int)target_height;
+	int x0 = x0in, y0 = y0in, x1 = x1in, y1 = y1in;
+	if (x0 < 0)
+		x0 = 0;
+	if (x1 < 0 || w < x1)
+		x1 = w;
+	if (y0 < 0)
+		y0 = 0;
+	if (y1 < 0 || h < y1)
+		y1 = h;
+	src->x0 = x0;
+	src->y0 = y0;
+	src->y1 = y1;
+	src->x1 = x1;
+	src->flags |= B200_CM_FLAG_ROI;
 }
 
 void b200_roi_tick(struct b200_roi_source *roi, struct b200_cm_source *cm)

@@ -41,7 +41,8 @@ def test_ring_orders_frames_and_drops_when_busy(shim, pkg):
                     ("pipeline_mutex", C.c_byte * 40), ("pipeline_cond", C.c_byte * 48),
                     ("pipeline_thread_running", C.c_bool), ("request_exit", C.c_bool), ("worker_busy", C.c_bool),
                     ("callback", C.c_void_p), ("callback_data", C.c_void_p), ("flags", C.c_uint32),
-                    ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong)]
+                    ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong),
+                    ("x0", C.c_int), ("x1", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
 
     cm = Cm()
     lib.b200_cm_create(C.byref(cm))
@@ -141,3 +142,48 @@ def test_roi_interleave_pacing(shim, pkg):
     assert on == [0, 2, 4, 6]                                        # every other tick
     assert all(s for i, t, s in staged if i == 0)                    # interleave off: every tick
     lib.b200_cm_destroy(cm)
+
+
+def test_roi_crop_is_staged_like_the_reference(shim, pkg):
+    """B200_CM_FLAG_ROI: the capture core stages only the ROI rectangle (common.c:272-291), clamped
+    like roi_send_range (roi.c:478-500); the callback sees a cx x cy surface, RGB rows then YUV rows."""
+    lib = shim
+    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+    W, H = 40, 24
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    yuv = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    flags_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16
+    cases = [((5, 3, 17, 20), (5, 3, 17, 20)),        # inside
+             ((-4, -1, 100, 9), (0, 0, W, 9)),        # negative / too large ends snap to the border
+             ((7, 2, -1, -1), (7, 2, W, H)),          # -1 = "to the end"
+             ((9, 9, 9, 12), None)]                   # empty rectangle: whole frame (common.c:273 fails)
+    for (x0, y0, x1, y1), want in cases:
+        cm = C.create_string_buffer(4096)
+        lib.b200_cm_create(cm)
+        got = []
+
+        def cb(_d, sd):
+            s = sd.contents
+            n = s.linesize * s.height
+            a = np.ctypeslib.as_array(C.cast(s.rgb_data, C.POINTER(C.c_uint8)), (n,)).copy()
+            b = np.ctypeslib.as_array(C.cast(s.yuv_data, C.POINTER(C.c_uint8)), (n,)).copy()
+            got.append((s.width, s.height, s.linesize, a, b))
+
+        cfn = CB(cb)
+        lib.b200_cm_request(cm, cfn, None)
+        C.c_uint32.from_buffer(cm, flags_off).value = 3   # CONVERT_RGB | CONVERT_YUV
+        lib.b200_cm_set_roi(cm, x0, y0, x1, y1, W, H)
+        assert C.c_uint32.from_buffer(cm, flags_off).value == 3 | 8
+        for _ in range(2):                                # one-frame staging latency: render twice
+            lib.b200_cm_tick(cm)
+            lib.b200_cm_render_target(cm, rgb.ctypes.data, yuv.ctypes.data, W * 4, W, H)
+            lib.b200_cm_drain(cm)
+        lib.b200_cm_destroy(cm)
+        assert got, "callback never ran"
+        w, h, ls, a, b = got[0]
+        ex0, ey0, ex1, ey1 = want if want else (0, 0, W, H)
+        assert (w, h) == (ex1 - ex0, ey1 - ey0)
+        assert ls == (W * 4 if (w, h) == (W, H) else w * 4)
+        assert np.array_equal(a.reshape(h, ls)[:, :w * 4], rgb[ey0:ey1, ex0:ex1].reshape(h, w * 4))
+        assert np.array_equal(b.reshape(h, ls)[:, :w * 4], yuv[ey0:ey1, ex0:ex1].reshape(h, w * 4))
