@@ -40,4 +40,5 @@ variants:
 	$(VARIANT) -DSCOPE_FAST_EMIT=0 -o variants_tmp/noemit.so
 	$(VARIANT) -DSCOPE_MAX_CHUNK=20 -o variants_tmp/chunk20.so
 	$(VARIANT) -DSCOPE_DEFER=0 -o variants_tmp/nodefer.so
+	$(VARIANT) -DSCOPE_RAWFLAT=1 -o variants_tmp/rawflat.so
 .PHONY: variants

@@ -47,6 +47,13 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_FAST_EMIT
 #define SCOPE_FAST_EMIT 1
 #endif
+//   SCOPE_RAWFLAT (experiment for round 2, OFF: written after this round's GPU budget was spent, not yet
+//                 run on a GPU) a 4 x 32 block whose 128 pixel words are all equal (solid regions,
+//                 letterbox bars) is accumulated from ONE pixel: one transform, three column-bin atomics
+//                 of +4 per lane, one vectorscope atomic of +128 per warp
+#ifndef SCOPE_RAWFLAT
+#define SCOPE_RAWFLAT 0
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -714,6 +721,9 @@ struct Prep {
 	uint32_t idx[N];   // vectorscope bin, U | V << 8
 	bool all_counted;  // warp-uniform: every pixel of the warp's N x 32 block counts
 	bool flat;         // warp-uniform: the whole block hits one vectorscope bin
+#if SCOPE_RAWFLAT
+	bool rawflat;      // warp-uniform: all N x 32 pixel words are equal; only element [0] is filled in
+#endif
 };
 
 template <int SRC, bool VSCOPE, bool SURFACE, int N>
@@ -721,6 +731,32 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 					     const uint32_t (&q)[N], Prep<N> &o)
 {
 	constexpr bool kTransform = !SURFACE && (VSCOPE || SRC == SRC_YUV);
+#if SCOPE_RAWFLAT
+	o.rawflat = false;
+	if (!SURFACE) { // everything below is a function of the pixel word alone
+		uint32_t d = 0;
+#pragma unroll
+		for (int k = 1; k < N; k++)
+			d |= p[0] ^ p[k];
+		const uint32_t p_lane0 = __shfl_sync(0xFFFFFFFFu, p[0], 0);
+		if (__all_sync(0xFFFFFFFFu, (d | (p[0] ^ p_lane0)) == 0u)) {
+			const uint32_t bgr[3] = {carrier<0>(p[0], c.magic), carrier<1>(p[0], c.magic), carrier<2>(p[0], c.magic)};
+			uint32_t h3[3] = {0u, 0u, 0u};
+			if (kTransform)
+				rgb_to_yuv_hi<SRC == SRC_YUV>(bgr, coef, h3);
+#pragma unroll
+			for (int j = 0; j < 3; j++)
+				o.cs[0][j] = SRC == SRC_RGB ? bgr[j] : carrier<2>(h3[j], c.magic);
+			o.a[0] = p[0];
+			// the fused YUV plane has alpha 255 everywhere (common.effect:30,41): only an RGB source looks at it
+			o.all_counted = SRC != SRC_RGB || p[0] > 0x00FFFFFFu;
+			o.idx[0] = __byte_perm(h3[0], h3[2], 0x3362);
+			o.flat = true;
+			o.rawflat = true;
+			return;
+		}
+	}
+#endif
 	uint32_t crgb[N][3]; // carriers of B, G, R
 	uint32_t hi[N][3];   // transform results: U, Y, V in byte 2
 	if (SRC == SRC_RGB || kTransform) {
@@ -784,6 +820,24 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 template <int SRC, bool VSCOPE, bool SURFACE, int N>
 __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o, uint32_t (&pend)[N])
 {
+#if SCOPE_RAWFLAT
+	if (o.rawflat) {
+		// N equal pixels per lane: each column bin gets +N once; a fully transparent block (RGB
+		// source, alpha 0) adds nothing to the bins but still counts for the vectorscope
+		if (SRC != SRC_NONE) {
+			const uint32_t n = o.all_counted ? (uint32_t)N : 0u;
+			if (c.bins_mask & 1u)
+				bins_add<true, false, false>(o.cs[0][0], o.cs[0][1], o.cs[0][2], c.wb0, c.wb1, n);
+			if (c.bins_mask & 2u)
+				bins_add<false, true, false>(o.cs[0][0], o.cs[0][1], o.cs[0][2], c.wb0, c.wb1, n);
+			if (c.bins_mask & 4u)
+				bins_add<false, false, true>(o.cs[0][0], o.cs[0][1], o.cs[0][2], c.wb0, c.wb1, n);
+		}
+		if (VSCOPE && c.lane == 0)
+			vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
+		return;
+	}
+#endif
 	if (SRC != SRC_NONE) {
 		if (o.all_counted && c.bins_mask == 7u) {
 #pragma unroll
