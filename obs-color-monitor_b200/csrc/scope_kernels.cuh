@@ -14,8 +14,10 @@
 //   - the CTA owns its 32 output columns exclusively and writes the final saturated
 //     u8 waveform directly (no zero-fill pass, no global atomics for the waveform).
 // Pixels arrive through TMA (cp.async.bulk.tensor) into a 4-stage shared-memory ring filled
-// by a producer warp; consumers read one 32-bit pixel per lane per row.  A plain-load kernel
-// covers planes TMA cannot describe.
+// by a producer warp; a consumer warp reads its 4 rows of a tile with one ldmatrix.x4 (one pixel
+// per lane per row).  A plain-load kernel covers planes TMA cannot describe.
+// The pass is bound by instruction issue, not by HBM or the LSU: every
+// instruction in the steady-state loop of tma_consume counts.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -364,11 +366,11 @@ __device__ __forceinline__ void bins_add(uint32_t cb, uint32_t cg, uint32_t cr, 
 //
 // Bank swizzle.  The plain word index U + 256 (V & 127) puts every bin of one U column in the
 // same bank (bank = U mod 32), and picture content has few distinct U values per 32-pixel row
-// segment: simulated on the "natural" test frames one warp-wide atomic then costs 11.3
-// conflict passes.  Replacing the low five bits by (U + 4 V) mod 32 spreads neighbouring
-// (U, V) pairs over the banks (4.9 passes, the floor set by lanes that hit the very SAME bin);
-// random content is unchanged (3.5).  For fixed V the map is a rotation of U's low bits, so it
-// is a bijection on the 15-bit word index; flush_vscope undoes it.
+// segment: simulated on the "natural" test frames one warp-wide atomic then costs 11.2
+// conflict passes (tools/vs_conflicts.py).  Mixing the low bits of V into the bank spreads
+// neighbouring (U, V) pairs over the banks (4.9 passes, the floor set by lanes that hit the very
+// SAME bin); random content is unchanged (3.5).  Two forms, both bijections on the 15-bit word
+// index that flush_vscope undoes: XOR (shipped) and the original (U + 4 V) mod 32.
 __device__ __forceinline__ uint32_t vs_word(uint32_t idx)
 {
 #if SCOPE_XORSWZ
