@@ -31,14 +31,24 @@ clean:
 	$(MAKE) -C oracle clean
 .PHONY: all product oracle clean
 
-# A/B builds for kernel work (tools/run_ab.sh benches every variants_tmp/*.so through SCOPE_LIB)
+# A/B builds for kernel work (tools/run_ab.sh runs the GPU parity tests on, and benches, every
+# variants_tmp/*.so through SCOPE_LIB).  `python tools/sass_budget.py variants_tmp/X.so` gives the static
+# instruction budget of a variant's steady-state loop without a GPU.  Names ending in _x are built with
+# SCOPE_EXPERIMENT: their two-plane (surface mode) rings do not fit, run_ab.sh skips those tests for them.
 VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
-variants:
+VARIANTS = w8 w12n8_x w12n6_x deepring nopipe rawflat w8_rawflat w8_deepring nofaddr nodefer
+FLAGS_w8 = -DSCOPE_TMA_WARPS=8
+FLAGS_w12n8_x = -DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=96
+FLAGS_w12n6_x = -DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=72
+FLAGS_deepring = -DSCOPE_DEEP_RING=1
+FLAGS_nopipe = -DSCOPE_PIPELINE=0
+FLAGS_rawflat = -DSCOPE_RAWFLAT=1
+FLAGS_w8_rawflat = -DSCOPE_TMA_WARPS=8 -DSCOPE_RAWFLAT=1
+FLAGS_w8_deepring = -DSCOPE_TMA_WARPS=8 -DSCOPE_DEEP_RING=1
+FLAGS_nofaddr = -DSCOPE_FADDR=0
+FLAGS_nodefer = -DSCOPE_DEFER=0
+variants: $(VARIANTS:%=variants_tmp/%.so)
+variants_tmp/%.so: $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh include/scope_ffi.h Makefile
 	@mkdir -p variants_tmp
-	$(VARIANT) -DSCOPE_LDSM=0 -DSCOPE_XORSWZ=0 -DSCOPE_DEFER=0 -DSCOPE_FADDR=0 -DSCOPE_FAST_EMIT=0 -o variants_tmp/base.so
-	$(VARIANT) -DSCOPE_FADDR=0 -o variants_tmp/nofaddr.so
-	$(VARIANT) -DSCOPE_FAST_EMIT=0 -o variants_tmp/noemit.so
-	$(VARIANT) -DSCOPE_MAX_CHUNK=20 -o variants_tmp/chunk20.so
-	$(VARIANT) -DSCOPE_DEFER=0 -o variants_tmp/nodefer.so
-	$(VARIANT) -DSCOPE_RAWFLAT=1 -o variants_tmp/rawflat.so
+	$(VARIANT) $(FLAGS_$*) -o $@
 .PHONY: variants

@@ -56,6 +56,19 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_RAWFLAT
 #define SCOPE_RAWFLAT 0
 #endif
+//   SCOPE_DEEP_RING (experiment for round 2, OFF) the tile ring takes all the shared memory the bins leave
+//                 instead of a fixed 32 KB: 8 stages = 64 KB in flight for the vectorscope-only pass
+//                 (one CTA per SM, no column bins), 6 stages = 48 KB per CTA for the passes without
+//                 the vectorscope (two CTAs per SM); the fused pass has no room to spare.  32 KB in
+//                 flight per SM caps a strip reader at ~3.9 TB/s (profiles/ubench_r01.md).
+#ifndef SCOPE_DEEP_RING
+#define SCOPE_DEEP_RING 0
+#endif
+//   SCOPE_PIPELINE 0 = no software pipeline over the interior tiles (prepare and commit of a tile back to
+//                 back, like the edge tiles): the A/B partner of the shipped commit(t) || prepare(t+1)
+#ifndef SCOPE_PIPELINE
+#define SCOPE_PIPELINE 1
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -86,7 +99,10 @@ constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
 #define SCOPE_MAX_CHUNK 10
 #endif
 constexpr int kMaxChunkItems = SCOPE_MAX_CHUNK; // upper bound of strips per dynamically claimed chunk
-constexpr int kQueue = 4;             // chunk mailbox entries {first strip, count} (producer is < kQueue chunks ahead)
+// chunk mailbox entries {first strip, count}.  The producer announces a chunk only after the stage of
+// its first tile was handed back, so it is at most kStages chunks ahead of the slowest consumer (chunks
+// of one single-tile strip): kQueue >= kStages (tools/ring_model.py checks the mailbox as well).
+constexpr int kQueue = SCOPE_DEEP_RING ? 8 : 4;
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
 constexpr int kVsWords = 32768;       // 65536 vectorscope bins, two u16 per word
@@ -203,20 +219,18 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
 template <int N>
 __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t (&p)[N])
 {
-	if (N == 2) {
-		asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
-			     : "=r"(p[0]), "=r"(p[1])
-			     : "r"(rows_addr + (uint32_t)(lane & 15) * 16u)
-			     : "memory");
-	} else {
-		// (callers only come here with N a multiple of 4)
+	// (callers only come here with N even: groups of four rows, then one pair if N % 4 == 2)
 #pragma unroll
-		for (int k = 0; k + 3 < N; k += 4)
-			asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-				     : "=r"(p[k]), "=r"(p[k + 1]), "=r"(p[k + 2]), "=r"(p[k + 3])
-				     : "r"(rows_addr + (uint32_t)k * 128u + (uint32_t)lane * 16u)
-				     : "memory");
-	}
+	for (int k = 0; k + 3 < N; k += 4)
+		asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+			     : "=r"(p[k]), "=r"(p[k + 1]), "=r"(p[k + 2]), "=r"(p[k + 3])
+			     : "r"(rows_addr + (uint32_t)k * 128u + (uint32_t)lane * 16u)
+			     : "memory");
+	if (N % 4 == 2)
+		asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+			     : "=r"(p[N - 2]), "=r"(p[N - 1])
+			     : "r"(rows_addr + (uint32_t)(N - 2) * 128u + (uint32_t)(lane & 15) * 16u)
+			     : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -312,11 +326,20 @@ struct SmemLayout {
 	static constexpr int kStageBytes = USE_TMA ? kPlanes * kTileBytes : 0;
 	// two planes per stage (surface mode) leave room for a 2-deep ring only
 	// as many stages as fit (two planes per stage in surface mode halve the depth)
+#if SCOPE_DEEP_RING
+	// what the bins leave of the SM's shared memory: 227 KB per CTA alone on an SM, half of 228 KB minus
+	// the 1 KB the system reserves per CTA when two CTAs share it; 512 B for barriers and the mailbox
+	static constexpr int kRing =
+		((VSCOPE || !(SRC == SRC_RGB || SURFACE)) ? 227 * 1024 : 113 * 1024) - kStageOff - 512;
+	static constexpr int kStagesFit = USE_TMA ? kRing / (kPlanes * kTileBytes) : 1;
+#else
 	static constexpr int kStagesFit = USE_TMA ? kRingBytes / (kPlanes * kTileBytes) : 1;
+#endif
 	static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : (kStagesFit < 2 ? 2 : kStagesFit);
 #ifndef SCOPE_EXPERIMENT
 	static_assert(!USE_TMA || kStagesFit >= 2, "tile too large for the ring");
 #endif
+	static_assert(!USE_TMA || kStages <= kQueue || kStages <= 4, "chunk mailbox shorter than the ring");
 	static constexpr int kBarOff = kStageOff + kStages * kStageBytes;
 	static constexpr int kQueueOff = kBarOff + (USE_TMA ? 2 * kMaxStages * 8 : 0);
 	static constexpr int kTotal = kQueueOff + (USE_TMA ? kQueue * 8 : 0) + 16;
@@ -742,6 +765,7 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 			d |= p[0] ^ p[k];
 		const uint32_t p_lane0 = __shfl_sync(0xFFFFFFFFu, p[0], 0);
 		if (__all_sync(0xFFFFFFFFu, (d | (p[0] ^ p_lane0)) == 0u)) {
+			// sass-cold{
 			const uint32_t bgr[3] = {carrier<0>(p[0], c.magic), carrier<1>(p[0], c.magic), carrier<2>(p[0], c.magic)};
 			uint32_t h3[3] = {0u, 0u, 0u};
 			if (kTransform)
@@ -756,6 +780,7 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 			o.flat = true;
 			o.rawflat = true;
 			return;
+			// sass-cold}
 		}
 	}
 #endif
@@ -824,6 +849,7 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 {
 #if SCOPE_RAWFLAT
 	if (o.rawflat) {
+		// sass-cold{
 		// N equal pixels per lane: each column bin gets +N once; a fully transparent block (RGB
 		// source, alpha 0) adds nothing to the bins but still counts for the vectorscope
 		if (SRC != SRC_NONE) {
@@ -838,6 +864,7 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 		if (VSCOPE && c.lane == 0)
 			vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
 		return;
+		// sass-cold}
 	}
 #endif
 	if (SRC != SRC_NONE) {
@@ -847,6 +874,7 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 				bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, 1u);
 		} else {
 			// some pixels transparent, or only some channels wanted (uniform branches)
+			// sass-cold{ (tools/sass_budget.py leaves these lines out of the fast-path count)
 #pragma unroll
 			for (int k = 0; k < N; k++) {
 				const uint32_t one = (o.all_counted || o.a[k] > 0x00FFFFFFu) ? 1u : 0u;
@@ -857,12 +885,15 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 				if (c.bins_mask & 4u)
 					bins_add<false, false, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, one);
 			}
+			// sass-cold}
 		}
 	}
 	if (VSCOPE) {
 		if (o.flat) {
+			// sass-cold{
 			if (c.lane == 0)
 				vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
+			// sass-cold}
 		} else {
 #pragma unroll
 			for (int k = 0; k < N; k++) {
@@ -883,12 +914,14 @@ __device__ __forceinline__ void commit_resolve(const TileCtx &c, const Prep<N> &
 		for (int k = 0; k < N; k++)
 			any |= pend[k];
 		if (any & 0x80008000u) {
+			// sass-cold{
 #pragma unroll
 			for (int k = 0; k < N; k++) {
 				const uint32_t h = o.idx[k] >> 15;
 				if (pend[k] & (h * 0x7FFF8000u + 0x8000u))
 					red_shared(vs_addr(c.vs_base, o.idx[k]), 0u - vs_one(o.idx[k]));
 			}
+			// sass-cold}
 		}
 	}
 }
@@ -1014,7 +1047,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					mbar_wait(bar_full + 8 * stage, phase);
 				skip_wait = false;
 				landed = 0;
-				if (SCOPE_LDSM && (N == 2 || N % 4 == 0)) {
+				if (SCOPE_LDSM && N % 2 == 0) {
 					const uint32_t rows =
 						smem_base + L::kStageOff + stage * L::kStageBytes + row0 * (kStripPx * 4);
 					if (kNeedP)
@@ -1060,7 +1093,17 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					mbar_arrive(bar + (dep & zero));
 			};
 			uint32_t t = 0;
-			if (n_full > 0) {
+			if (!SCOPE_PIPELINE) {
+				for (; t < n_full; t++) { // sass-loop (only in SCOPE_PIPELINE=0 builds)
+					uint32_t p[N], q[N];
+					Prep<N> E;
+					const uint32_t bar = fetch_tile(p, q);
+					release_tile(bar, p, q);
+					peek_tile();
+					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, E);
+					commit_tile<R_SRC, R_VS, SURFACE, N>(tc, E);
+				}
+			} else if (n_full > 0) {
 				// software pipeline over the interior tiles: atomics of tile t next to the
 				// arithmetic of tile t+1 (two Prep register sets, ping-pong); the vectorscope's
 				// overflow check of tile t is looked at after that arithmetic (SCOPE_DEFER)
@@ -1079,7 +1122,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				release_tile(bar, p, q);
 				peek_tile();
 				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
-				for (t = 1; t + 1 < n_full; t += 2) {
+				for (t = 1; t + 1 < n_full; t += 2) { // sass-loop (tools/sass_budget.py: the steady state)
 					bar = fetch_tile(p, q);
 					issue(A);
 					release_tile(bar, p, q);

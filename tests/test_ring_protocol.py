@@ -32,6 +32,25 @@ def test_tile_walk(stages):
             rm.run("tiles", 16, stages, tiles, rm.make_chunks(rng.randint(1, 5), rng), seed)
 
 
+def test_chunk_mailbox_must_be_as_long_as_the_ring():
+    """The producer announces a chunk once the stage of its first tile is free, so with single-tile
+    strips in single-strip chunks it runs kStages announcements ahead of the slowest consumer: a
+    4-entry mailbox is lapped by an 8-stage ring (SCOPE_DEEP_RING builds use kQueue = 8), never by a
+    4-stage one."""
+    chunks = [(i, 1) for i in range(40)]
+    for seed in range(10):
+        rm.run("tiles", 16, 4, 1, chunks, seed, kqueue=4)
+        rm.run("tiles", 16, 8, 1, chunks, seed, kqueue=8)
+        rm.run("tiles", 8, 8, 2, chunks, seed, kqueue=8)
+    lapped = 0
+    for seed in range(30):
+        try:
+            rm.run("tiles", 16, 8, 1, chunks, seed, kqueue=4)
+        except rm.ProtocolError:
+            lapped += 1
+    assert lapped > 0
+
+
 def test_model_rejects_a_walk_that_skips_tiles():
     """The first draft of the row-group walk let a warp wait only for the tiles it owns a group in
     (one arrival per group).  A warp can then fall two phases behind a barrier it does not take
@@ -43,7 +62,7 @@ def test_model_rejects_a_walk_that_skips_tiles():
         while True:
             while not ring.full[tile_seq % S].test((tile_seq // S) & 1):
                 yield
-            first, count = queue[qr % kqueue]
+            first, count = rm.read_mailbox(queue, qr, kqueue)
             qr += 1
             if count == 0:
                 return

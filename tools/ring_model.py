@@ -87,7 +87,7 @@ def producer(ring: Ring, chunks: list, tiles_per_strip: int, queue: list, kqueue
     for first, count in chunks + [(None, 0)]:
         while not ring.empty[stage].test(phase ^ 1):
             yield "producer waits empty (chunk)"
-        queue[qw % kqueue] = (first, count)
+        queue[qw % kqueue] = (first, count, qw)   # (the sequence number only exists in the model)
         qw += 1
         if count == 0:
             ring.full[stage].arrive()
@@ -107,6 +107,15 @@ def producer(ring: Ring, chunks: list, tiles_per_strip: int, queue: list, kqueue
                 yield "producer issued"
 
 
+def read_mailbox(queue: list, qr: int, kqueue: int):
+    """a consumer's read of chunk announcement number qr: the entry must still be that chunk's (the
+    producer must not have lapped the mailbox: kQueue >= kStages in scope_kernels.cuh)"""
+    first, count, seq = queue[qr % kqueue]
+    if seq != qr:
+        raise ProtocolError(f"chunk mailbox entry {qr % kqueue} overwritten: expected announcement {qr}, found {seq}")
+    return first, count
+
+
 def land_one(ring: Ring, rng: random.Random):
     """one in-flight TMA load completes (any of them: completions may be reordered)"""
     stage, tile = ring.in_flight.pop(rng.randrange(len(ring.in_flight)))
@@ -122,7 +131,7 @@ def consumer_tiles(ring: Ring, warp: int, tiles_per_strip: int, queue: list, kqu
     while True:
         while not ring.full[stage].test(phase):
             yield "consumer waits chunk"
-        first, count = queue[qr % kqueue]
+        first, count = read_mailbox(queue, qr, kqueue)
         qr += 1
         if count == 0:
             return
@@ -185,7 +194,7 @@ def consumer_groups(ring: Ring, warp: int, nwork: int, gpt: int, tiles_per_strip
     groups = tiles_per_strip * gpt
     while True:
         yield from advance_to(tile_seq)
-        first, count = queue[qr % kqueue]
+        first, count = read_mailbox(queue, qr, kqueue)
         qr += 1
         if count == 0:
             return
