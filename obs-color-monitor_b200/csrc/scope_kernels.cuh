@@ -69,6 +69,14 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_PIPELINE
 #define SCOPE_PIPELINE 1
 #endif
+//   SCOPE_STRAIGHT (experiment for round 2, OFF) the steady state of an ordinary tile (all pixels counted,
+//                 all three channels, block not flat) is ONE basic block: stage handed back first, then
+//                 the atomics of tile t and the arithmetic of tile t+1 with no branch between them, so
+//                 that ptxas can spread the 16 atomics over the ~100 arithmetic instructions instead of
+//                 issuing them as a burst that fills the LSU queue while the other pipes idle
+#ifndef SCOPE_STRAIGHT
+#define SCOPE_STRAIGHT 0
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -903,6 +911,20 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 	}
 }
 
+// the atomics of an ordinary tile and nothing else (no branch): the caller has checked all_counted,
+// !flat (and !rawflat) and bins_mask == 7
+template <int SRC, bool VSCOPE, bool SURFACE, int N>
+__device__ __forceinline__ void commit_issue_fast(const TileCtx &c, const Prep<N> &o, uint32_t (&pend)[N])
+{
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		if (SRC != SRC_NONE)
+			bins_add<true, true, true>(o.cs[k][0], o.cs[k][1], o.cs[k][2], c.wb0, c.wb1, 1u);
+		if (VSCOPE)
+			pend[k] = atom_shared_add(vs_addr(c.vs_base, o.idx[k]), vs_one(o.idx[k]));
+	}
+}
+
 template <int SRC, bool VSCOPE, bool SURFACE, int N>
 __device__ __forceinline__ void commit_resolve(const TileCtx &c, const Prep<N> &o, const uint32_t (&pend)[N])
 {
@@ -1122,6 +1144,38 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				release_tile(bar, p, q);
 				peek_tile();
 				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
+#if SCOPE_STRAIGHT
+				// one step: the atomics of `cur`, the arithmetic of `nxt`.  Ordinary tile: one basic block.
+				auto step = [&](const Prep<N> &cur, Prep<N> &nxt) {
+					const uint32_t bar2 = fetch_tile(p, q);
+					bool ordinary = !cur.flat && (R_SRC == SRC_NONE || (cur.all_counted && tc.bins_mask == 7u));
+#if SCOPE_RAWFLAT
+					ordinary = ordinary && !cur.rawflat;
+#endif
+					if (ordinary) {
+						release_tile(bar2, p, q);
+						peek_tile();
+						commit_issue_fast<R_SRC, R_VS, SURFACE, N>(tc, cur, pend);
+						if (!SCOPE_DEFER)
+							commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, cur, pend);
+						prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, nxt);
+					} else {
+						// sass-cold{
+						commit_issue<R_SRC, R_VS, SURFACE, N>(tc, cur, pend);
+						if (!SCOPE_DEFER)
+							commit_resolve<R_SRC, R_VS, SURFACE, N>(tc, cur, pend);
+						release_tile(bar2, p, q);
+						peek_tile();
+						prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, nxt);
+						// sass-cold}
+					}
+					resolve(cur);
+				};
+				for (t = 1; t + 1 < n_full; t += 2) { // sass-loop
+					step(A, B);
+					step(B, A);
+				}
+#else
 				for (t = 1; t + 1 < n_full; t += 2) { // sass-loop (tools/sass_budget.py: the steady state)
 					bar = fetch_tile(p, q);
 					issue(A);
@@ -1136,6 +1190,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
 					resolve(B);
 				}
+#endif
 				if (t < n_full) {
 					bar = fetch_tile(p, q);
 					issue(A);
