@@ -103,7 +103,8 @@ struct scope_params {
 struct scope_out_host {
 	uint32_t *hist_counts;   /* [1024] raw counts */
 	float *hist_float;       /* [1024] what the reference uploads as GS_RGBA32F (linear or log) */
-	uint32_t *hist_max;      /* [3]    hi_max after the post-pass */
+	uint32_t *hist_max;      /* [3]    hi_max after the post-pass; left untouched when hist_components selects
+				  * no plane (no bit of 0x77), like his_draw_histogram's early return, histogram.c:366-373 */
 	uint8_t *wave;           /* [256*width*4] */
 	uint8_t *vscope;         /* [65536] */
 	uint8_t *wave_display;   /* [256*width*4] intensity applied (needs wave_intensity > 0) */

@@ -527,7 +527,9 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 		CU_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}
-	if (want_hist && out->hist_max) {
+	// (no component bit selects a plane: the reference returns before its level pass, histogram.c:366-373,
+	// and hi_max keeps its previous contents - so nothing is written here either)
+	if (want_hist && out->hist_max && (pr->hist_components & 0x77u)) {
 		hist_max_kernel<<<n_frames, 256, 0, stream>>>(hist, hist_stride, out->hist_max, pr->hist_components,
 							       s->width, s->height, pr->level_fixed_value,
 							       pr->level_ratio_value);
@@ -723,7 +725,7 @@ int wait_host(scope_ctx *ctx, int slot, const scope_out_host *out)
 				if (pr.hist_components & (uint32_t)mask)
 					hi[j] = 1;
 		}
-		if (out->hist_max)
+		if (out->hist_max && (pr.hist_components & 0x77u)) // else untouched, like histogram.c:366-373
 			memcpy(out->hist_max, hi, sizeof hi);
 	}
 	if (pr.scopes & SCOPE_VSCOPE) {
@@ -1023,7 +1025,7 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32
 		if (out->hist_counts && out->hist_counts != partial->hist_counts)
 			CU_TRY(ctx, cudaMemcpyAsync(out->hist_counts, partial->hist_counts, 4096, cudaMemcpyDeviceToDevice,
 						    st));
-		if (out->hist_max) {
+		if (out->hist_max && (pr->hist_components & 0x77u)) {
 			hist_max_kernel<<<1, 256, 0, st>>>(partial->hist_counts, 1024, out->hist_max, pr->hist_components,
 							    full_width, full_height, pr->level_fixed_value,
 							    pr->level_ratio_value);

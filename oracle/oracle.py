@@ -86,6 +86,9 @@ class Oracle:
         L.orc_histogram_post.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_histogram_post.restype = None
+        L.orc_draw_histogram.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_Surface), C.c_void_p,
+                                         C.c_void_p]
+        L.orc_draw_histogram.restype = None
         L.orc_waveform.argtypes = [C.c_uint32, C.POINTER(_Surface), C.c_void_p]
         L.orc_waveform.restype = None
         L.orc_vectorscope.argtypes = [C.POINTER(_Surface), C.c_void_p]
@@ -126,6 +129,17 @@ class Oracle:
         hi = np.zeros(3, np.uint32)
         self.lib.orc_histogram_post(components, width, height, level_fixed, level_ratio, int(logscale),
                                     counts.ctypes.data, out.ctypes.data, hi.ctypes.data)
+        return out, hi
+
+    def draw_histogram(self, components, rgb=None, yuv=None, width=None, height=None, colorspace=2,
+                       level_fixed=0, level_ratio=0, logscale=False, hi_init=(0, 0, 0)):
+        """his_draw_histogram as a whole: (float32[1024], hi_max u32[3]); hi_max starts as ``hi_init`` and is
+        left alone when no plane is selected (histogram.c:366-373)."""
+        s, _, _, _ = _surface(rgb, yuv, width, height, colorspace)
+        out = np.zeros(1024, np.float32)
+        hi = np.array(hi_init, np.uint32)
+        self.lib.orc_draw_histogram(components, level_fixed, level_ratio, int(logscale), C.byref(s),
+                                    out.ctypes.data, hi.ctypes.data)
         return out, hi
 
     def waveform(self, components, rgb=None, yuv=None, width=None, height=None, colorspace=2):
@@ -198,11 +212,11 @@ class Ref:
         return os.path.exists(REF_SO)
 
     def histogram(self, components, rgb=None, yuv=None, width=None, height=None, colorspace=2,
-                  level_fixed=0, level_ratio=0, logscale=False):
-        """Returns (float32[1024] as the reference leaves tex_buf, hi_max u32[3])."""
+                  level_fixed=0, level_ratio=0, logscale=False, hi_init=(0, 0, 0)):
+        """Returns (float32[1024] as the reference leaves tex_buf, hi_max u32[3] starting as hi_init)."""
         _, ls, w, h = _surface(rgb, yuv, width, height, colorspace)
         out = np.zeros(1024, np.float32)
-        hi = np.zeros(3, np.uint32)
+        hi = np.array(hi_init, np.uint32)
         self.lib.ref_his_draw_histogram(components, level_fixed, level_ratio, int(logscale), _ptr(rgb), _ptr(yuv),
                                         ls, w, h, colorspace, out.ctypes.data, hi.ctypes.data)
         return out, hi

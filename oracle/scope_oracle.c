@@ -317,6 +317,23 @@ ORC_API void orc_histogram_post(uint32_t components, uint32_t width, uint32_t he
 	}
 }
 
+/* his_draw_histogram as a whole (histogram.c:357-418), for callers that want the reference's exact
+ * buffer state: when `components` selects no plane, or the selected plane is NULL, the reference
+ * returns right after zeroing the buffer (histogram.c:366-373) - the level pass is never reached and
+ * hi_max keeps whatever the caller had in it. */
+ORC_API void orc_draw_histogram(uint32_t components, int level_fixed_value, int level_ratio_value, int logscale,
+				const struct orc_surface *s, float out[NBINS * 4], uint32_t hi_max[3])
+{
+	uint32_t dbuf[NBINS * 4];
+	orc_histogram_counts(components, s, dbuf);
+	if (!pick_plane(components, s)) {
+		memset(out, 0, sizeof(float) * NBINS * 4);
+		return;
+	}
+	orc_histogram_post(components, s->width, s->height, level_fixed_value, level_ratio_value, logscale, dbuf, out,
+			   hi_max);
+}
+
 /* ------------------------------------------------------------------ */
 /* waveform: dbuf = u8 [256][width][4], row 0 = value 255, byte 3 = 0   */
 /* ------------------------------------------------------------------ */
