@@ -86,6 +86,12 @@ void b200_his_surface_cb(void *data, struct cm_surface_data *surface_data);
 void b200_wvs_surface_cb(void *data, struct cm_surface_data *surface_data);
 void b200_vss_surface_cb(void *data, struct cm_surface_data *surface_data);
 
+/* the callbacks' early-return rules (histogram.c:436-441, waveform.c:276-281, vectorscope.c:252-253): true =
+ * the callback returns without touching its buffers and without flipping w_tex_buf */
+bool b200_his_inputs_missing(const struct b200_his_source *src, const struct cm_surface_data *surface_data);
+bool b200_wvs_inputs_missing(const struct b200_wvs_source *src, const struct cm_surface_data *surface_data);
+bool b200_vss_inputs_missing(const struct b200_vss_source *src, const struct cm_surface_data *surface_data);
+
 /* ---- ROI fan-out: one surface, every registered scope — as ONE fused GPU pass ---- */
 #define B200_ROI_MAX_SOURCES 8
 struct b200_roi_source {

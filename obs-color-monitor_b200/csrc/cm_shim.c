@@ -41,15 +41,16 @@ void b200_his_destroy(struct b200_his_source *src)
 	src->tex_buf[0] = src->tex_buf[1] = NULL;
 }
 
-static bool his_inputs_missing(const struct b200_his_source *src, const struct cm_surface_data *sd)
+bool b200_his_inputs_missing(const struct b200_his_source *src, const struct cm_surface_data *sd)
 {
-	/* histogram.c:436-441; in fused mode the YUV plane is made on the GPU from rgb_data */
+	/* histogram.c:436-441, including the case of both RGB and YUV bits set (a missing YUV plane then
+	 * stops the callback although the RGB plane would be the one read).  In fused mode the YUV
+	 * plane is made on the GPU from rgb_data. */
+	const void *yuv = src->mode == SCOPE_MODE_FUSED ? sd->rgb_data : sd->yuv_data;
 	if ((src->components & SCOPE_COMP_RGB) && !sd->rgb_data)
 		return true;
-	if (!(src->components & SCOPE_COMP_RGB) && (src->components & SCOPE_COMP_YUV)) {
-		if (src->mode == SCOPE_MODE_FUSED ? !sd->rgb_data : !sd->yuv_data)
-			return true;
-	}
+	if ((src->components & SCOPE_COMP_YUV) && !yuv)
+		return true;
 	return sd->width == 0;
 }
 
@@ -67,13 +68,29 @@ static void his_params(const struct b200_his_source *src, struct scope_params *p
 void b200_his_surface_cb(void *data, struct cm_surface_data *sd)
 {
 	struct b200_his_source *src = data;
-	if (his_inputs_missing(src, sd))
+	if (b200_his_inputs_missing(src, sd))
 		return;
 	const int w = src->w_tex_buf;
 	if (!src->tex_buf[w])
 		src->tex_buf[w] = zalloc(sizeof(float) * B200_HI_SIZE * 4);
 	if (!src->tex_buf[w])
 		return;
+	if (sd->height == 0) {
+		/* No rows: the reference's pixel loop does not iterate (histogram.c:379-395), so the
+		 * buffer stays zero - as u32, as float and on the log scale alike - the level pass runs
+		 * on zero counts (histogram.c:397-402, 412) and the buffer is flipped.  Nothing for the
+		 * GPU to do. */
+		memset(src->tex_buf[w], 0, sizeof(float) * B200_HI_SIZE * 4);
+		if (src->components & (SCOPE_COMP_RGB | SCOPE_COMP_YUV)) {
+			uint32_t v = 1; /* his_calculate_max on zero counts; W*H*ratio/1000 = 0 is raised to 1 too */
+			if (src->level_fixed_value > 0)
+				v = (uint32_t)src->level_fixed_value;
+			for (int j = 0, mask = 0x44; j < 3; j++, mask >>= 1)
+				src->hi_max[w][j] = (src->logscale && (src->components & (uint32_t)mask)) ? 1u : v;
+		}
+		src->w_tex_buf = w ^ 1;
+		return;
+	}
 
 	struct scope_params p;
 	his_params(src, &p);
@@ -118,27 +135,32 @@ static void wvs_ensure_tex_buf_size(struct b200_wvs_source *src, uint32_t width,
 	src->tex_buf_width[ix] = width;
 }
 
-static bool wvs_inputs_missing(const struct b200_wvs_source *src, const struct cm_surface_data *sd)
+bool b200_wvs_inputs_missing(const struct b200_wvs_source *src, const struct cm_surface_data *sd)
 {
-	/* waveform.c:276-281 */
+	/* waveform.c:276-281 (same rule as the histogram's) */
+	const void *yuv = src->mode == SCOPE_MODE_FUSED ? sd->rgb_data : sd->yuv_data;
 	if ((src->components & SCOPE_COMP_RGB) && !sd->rgb_data)
 		return true;
-	if (!(src->components & SCOPE_COMP_RGB) && (src->components & SCOPE_COMP_YUV)) {
-		if (src->mode == SCOPE_MODE_FUSED ? !sd->rgb_data : !sd->yuv_data)
-			return true;
-	}
+	if ((src->components & SCOPE_COMP_YUV) && !yuv)
+		return true;
 	return sd->width == 0;
 }
 
 void b200_wvs_surface_cb(void *data, struct cm_surface_data *sd)
 {
 	struct b200_wvs_source *src = data;
-	if (wvs_inputs_missing(src, sd))
+	if (b200_wvs_inputs_missing(src, sd))
 		return;
 	const int w = src->w_tex_buf;
 	wvs_ensure_tex_buf_size(src, sd->width, w);
 	if (!src->tex_buf[w])
 		return;
+	if (sd->height == 0) {
+		/* no rows: zero-filled image and a flip (waveform.c:225-226, 240, 288) */
+		memset(src->tex_buf[w], 0, (size_t)sd->width * B200_WV_SIZE * 4);
+		src->w_tex_buf = w ^ 1;
+		return;
+	}
 
 	struct scope_params p;
 	memset(&p, 0, sizeof(p));
@@ -172,16 +194,16 @@ void b200_vss_destroy(struct b200_vss_source *src)
 	src->tex_buf[0] = src->tex_buf[1] = NULL;
 }
 
-static bool vss_inputs_missing(const struct b200_vss_source *src, const struct cm_surface_data *sd)
+bool b200_vss_inputs_missing(const struct b200_vss_source *src, const struct cm_surface_data *sd)
 {
-	/* vectorscope.c:252-253 */
+	/* vectorscope.c:252-253: only the plane is tested; an empty surface is still processed */
 	return src->mode == SCOPE_MODE_FUSED ? !sd->rgb_data : !sd->yuv_data;
 }
 
 void b200_vss_surface_cb(void *data, struct cm_surface_data *sd)
 {
 	struct b200_vss_source *src = data;
-	if (vss_inputs_missing(src, sd))
+	if (b200_vss_inputs_missing(src, sd))
 		return;
 	if (sd->width == 0 || sd->height == 0) {
 		/* the reference zero-fills and flips even for an empty surface (vectorscope.c:219-236) */
@@ -263,14 +285,22 @@ void b200_roi_surface_cb(void *data, struct cm_surface_data *sd)
 	struct b200_his_source *his = roi->n_his ? roi->his[0] : NULL;
 	struct b200_wvs_source *wvs = roi->n_wvs ? roi->wvs[0] : NULL;
 	struct b200_vss_source *vss = roi->n_vss ? roi->vss[0] : NULL;
-	if (his && his_inputs_missing(his, sd))
+	if (his && b200_his_inputs_missing(his, sd))
 		his = NULL;
-	if (wvs && wvs_inputs_missing(wvs, sd))
+	if (wvs && b200_wvs_inputs_missing(wvs, sd))
 		wvs = NULL;
-	if (vss && (vss_inputs_missing(vss, sd) || sd->width == 0 || sd->height == 0))
+	if (vss && b200_vss_inputs_missing(vss, sd))
 		vss = NULL;
 
-	if (sd->height != 0 && (his || wvs || vss)) {
+	if (sd->width == 0 || sd->height == 0) {
+		/* an empty surface never reaches the GPU: each callback files its zeroed result itself */
+		if (his)
+			b200_his_surface_cb(his, sd);
+		if (wvs)
+			b200_wvs_surface_cb(wvs, sd);
+		if (vss)
+			b200_vss_surface_cb(vss, sd);
+	} else if (his || wvs || vss) {
 		struct scope_params p;
 		memset(&p, 0, sizeof(p));
 		p.mode = roi->mode;
@@ -315,8 +345,6 @@ void b200_roi_surface_cb(void *data, struct cm_surface_data *sd)
 				vss->w_tex_buf = vw ^ 1;
 			}
 		}
-	} else if (vss && roi->n_vss) {
-		b200_vss_surface_cb(roi->vss[0], sd);
 	}
 
 	/* any further sources of the same kind: their own pass, like the reference's loop */

@@ -187,3 +187,142 @@ def test_roi_crop_is_staged_like_the_reference(shim, pkg):
         assert ls == (W * 4 if (w, h) == (W, H) else w * 4)
         assert np.array_equal(a.reshape(h, ls)[:, :w * 4], rgb[ey0:ey1, ex0:ex1].reshape(h, w * 4))
         assert np.array_equal(b.reshape(h, ls)[:, :w * 4], yuv[ey0:ey1, ex0:ex1].reshape(h, w * 4))
+
+
+def test_callback_early_returns_match_the_reference(shim, ref):
+    """The shim's b200_*_inputs_missing predicates (what makes a callback return without touching its
+    buffers) against the reference's own his/wvs/vss_surface_cb compiled from its sources
+    (oracle/_ref): the reference processed a surface iff it flipped w_tex_buf.  Whole truth table:
+    components incl. none / both planes' bits, each plane present or NULL, empty surfaces."""
+    lib, L = shim, ref.lib
+    for n in ("b200_his_inputs_missing", "b200_wvs_inputs_missing", "b200_vss_inputs_missing"):
+        getattr(lib, n).restype = C.c_bool
+        getattr(lib, n).argtypes = [C.c_void_p, C.POINTER(SurfaceData)]
+    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
+    rgb = np.full((3, 16), 200, np.uint8)
+    yuv = np.full((3, 16), 90, np.uint8)
+    scratch = np.zeros(256 * 16 * 4 + 65536, np.uint8)
+    aux = (C.c_uint32 * 4)()
+    n_cases = 0
+    for comp in (0x00, 0x07, 0x20, 0x50, 0x70, 0x77, 0x13, 0x08):
+        for has_rgb in (False, True):
+            for has_yuv in (False, True):
+                for w, h in ((4, 3), (0, 3), (4, 0), (0, 0)):
+                    sd = SurfaceData(rgb.ctypes.data if has_rgb else None, yuv.ctypes.data if has_yuv else None,
+                                     16, w, h, 2, None)
+                    args = (sd.rgb_data, sd.yuv_data, 16, w, h, 2, scratch.ctypes.data, C.cast(aux, C.c_void_p))
+                    # reference: a fresh source starts with w_tex_buf = 0; 1 afterwards = processed
+                    st = L.ref_his_new(comp, 0, 0, 0)
+                    ref_his = L.ref_his_surface_cb(st, *args) == 1
+                    L.ref_his_free(st)
+                    st = L.ref_wvs_new(comp)
+                    ref_wvs = L.ref_wvs_surface_cb(st, *args) == 1
+                    L.ref_wvs_free(st)
+                    st = L.ref_vss_new()
+                    ref_vss = L.ref_vss_surface_cb(st, *args) == 1
+                    L.ref_vss_free(st)
+                    src = C.create_string_buffer(512)
+                    lib.b200_his_init(src, None, comp)
+                    assert lib.b200_his_inputs_missing(src, C.byref(sd)) == (not ref_his), (hex(comp), has_rgb, has_yuv, w, h)
+                    lib.b200_wvs_init(src, None, comp)
+                    assert lib.b200_wvs_inputs_missing(src, C.byref(sd)) == (not ref_wvs), (hex(comp), has_rgb, has_yuv, w, h)
+                    lib.b200_vss_init(src, None)
+                    assert lib.b200_vss_inputs_missing(src, C.byref(sd)) == (not ref_vss), (has_rgb, has_yuv, w, h)
+                    n_cases += 1
+    assert n_cases == 8 * 2 * 2 * 4
+
+
+class _His(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("components", C.c_uint32), ("level_fixed_value", C.c_int),
+                ("level_ratio_value", C.c_int), ("logscale", C.c_bool), ("tex_buf", C.c_void_p * 2),
+                ("hi_max", (C.c_uint32 * 3) * 2), ("w_tex_buf", C.c_int)]
+
+
+class _Wvs(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("components", C.c_uint32), ("tex_buf", C.c_void_p * 2),
+                ("tex_buf_width", C.c_uint32 * 2), ("w_tex_buf", C.c_int)]
+
+
+class _Vss(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("tex_buf", C.c_void_p * 2), ("tex_cs", C.c_int * 2),
+                ("w_tex_buf", C.c_int)]
+
+
+def test_empty_surfaces_match_the_reference(shim, ref):
+    """Surfaces without rows (or without columns) never reach the GPU: the shim files the result the
+    reference's loops leave when they do not iterate - zeroed buffer, level pass on zero counts, flip -
+    or does nothing when the reference's callback returns early.  Compared field by field with the
+    reference's own callbacks (oracle/_ref), standalone and through the ROI fan-out."""
+    lib, L = shim, ref.lib
+    for n in ("b200_his_surface_cb", "b200_wvs_surface_cb", "b200_vss_surface_cb", "b200_roi_surface_cb"):
+        getattr(lib, n).argtypes = [C.c_void_p, C.POINTER(SurfaceData)]
+        getattr(lib, n).restype = None
+    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    for n in ("his", "wvs", "vss"):
+        getattr(lib, f"b200_roi_register_{n}").argtypes = [C.c_void_p, C.c_void_p]
+        getattr(lib, f"b200_{n}_destroy").argtypes = [C.c_void_p]
+    lib.b200_roi_destroy.argtypes = [C.c_void_p]
+    rgb = np.full((3, 16), 200, np.uint8)
+    yuv = np.full((3, 16), 90, np.uint8)
+    n_flips = 0
+    for via_roi in (False, True):
+        for comp in (0x00, 0x07, 0x20, 0x70, 0x77):
+            for has_rgb, has_yuv in ((True, True), (True, False), (False, True)):
+                for w, h in ((4, 0), (0, 3), (0, 0)):
+                    for fixed, ratio, log in ((0, 0, 0), (77, 0, 0), (0, 9, 1), (77, 9, 1)):
+                        sd = SurfaceData(rgb.ctypes.data if has_rgb else None, yuv.ctypes.data if has_yuv else None,
+                                         16, w, h, 1, None)
+                        args = (sd.rgb_data, sd.yuv_data, 16, w, h, 1)
+                        # --- the reference ---
+                        hbuf, hmax = np.full(1024, 7, np.uint32), np.full(3, 7, np.uint32)
+                        st = L.ref_his_new(comp, fixed, ratio, log)
+                        r_his = L.ref_his_surface_cb(st, *args, hbuf.ctypes.data, hmax.ctypes.data)
+                        L.ref_his_free(st)
+                        wbuf, wwidth = np.full(256 * 16 * 4, 7, np.uint8), C.c_uint32(99)
+                        st = L.ref_wvs_new(comp)
+                        r_wvs = L.ref_wvs_surface_cb(st, *args, wbuf.ctypes.data, C.cast(C.byref(wwidth), C.c_void_p))
+                        L.ref_wvs_free(st)
+                        vbuf, vcs = np.full(65536, 7, np.uint8), C.c_int(99)
+                        st = L.ref_vss_new()
+                        r_vss = L.ref_vss_surface_cb(st, *args, vbuf.ctypes.data, C.cast(C.byref(vcs), C.c_void_p))
+                        L.ref_vss_free(st)
+                        # --- the shim (no GPU context: none of these cases may need one) ---
+                        his, wvs, vss = _His(), _Wvs(), _Vss()
+                        lib.b200_his_init(C.byref(his), None, comp)
+                        his.level_fixed_value, his.level_ratio_value, his.logscale = fixed, ratio, bool(log)
+                        lib.b200_wvs_init(C.byref(wvs), None, comp)
+                        lib.b200_vss_init(C.byref(vss), None)
+                        if via_roi:
+                            roi = C.create_string_buffer(1024)
+                            lib.b200_roi_init(roi, None, 1)      # SCOPE_MODE_SURFACE
+                            lib.b200_roi_register_his(roi, C.byref(his))
+                            lib.b200_roi_register_wvs(roi, C.byref(wvs))
+                            lib.b200_roi_register_vss(roi, C.byref(vss))
+                            lib.b200_roi_surface_cb(roi, C.byref(sd))
+                            lib.b200_roi_destroy(roi)
+                        else:
+                            lib.b200_his_surface_cb(C.byref(his), C.byref(sd))
+                            lib.b200_wvs_surface_cb(C.byref(wvs), C.byref(sd))
+                            lib.b200_vss_surface_cb(C.byref(vss), C.byref(sd))
+                        case = (via_roi, hex(comp), has_rgb, has_yuv, w, h, fixed, ratio, log)
+                        assert his.w_tex_buf == r_his and wvs.w_tex_buf == r_wvs and vss.w_tex_buf == r_vss, case
+                        if r_his:
+                            got = np.ctypeslib.as_array(C.cast(his.tex_buf[0], C.POINTER(C.c_uint32)), (1024,))
+                            assert np.array_equal(got, hbuf) and list(his.hi_max[0]) == list(hmax), case
+                        if r_wvs:
+                            assert wvs.tex_buf_width[0] == wwidth.value == w, case
+                            got = np.ctypeslib.as_array(C.cast(wvs.tex_buf[0], C.POINTER(C.c_uint8)), (256 * w * 4,))
+                            assert np.array_equal(got, wbuf[:256 * w * 4]), case
+                        if r_vss:
+                            got = np.ctypeslib.as_array(C.cast(vss.tex_buf[0], C.POINTER(C.c_uint8)), (65536,))
+                            assert np.array_equal(got, vbuf) and vss.tex_cs[0] == vcs.value == 1, case
+                        n_flips += r_his + r_wvs + r_vss
+                        lib.b200_his_destroy(C.byref(his))
+                        lib.b200_wvs_destroy(C.byref(wvs))
+                        lib.b200_vss_destroy(C.byref(vss))
+    assert n_flips > 100
