@@ -112,6 +112,11 @@ struct b200_roi_source {
 };
 
 void b200_roi_init(struct b200_roi_source *roi, scope_ctx *ctx, uint32_t mode);
+/* what the ROI's capture core has to stage for the scopes registered on it: roi_tick's
+ * ROI | RAW_TEXTURE | OR of the consumers' CONVERT flags (roi.c:533-540), each consumer's flags by the rule of
+ * its own update function (histogram.c:120-121, waveform.c:101-102, vectorscope.c:79).  In SCOPE_MODE_FUSED the
+ * YUV plane is made on the GPU: any consumer needs the RGB plane and nobody needs CONVERT_YUV. */
+uint32_t b200_roi_capture_flags(struct b200_roi_source *roi);
 void b200_roi_destroy(struct b200_roi_source *roi);
 int b200_roi_register_his(struct b200_roi_source *roi, struct b200_his_source *src);
 int b200_roi_register_wvs(struct b200_roi_source *roi, struct b200_wvs_source *src);
@@ -122,6 +127,7 @@ void b200_roi_surface_cb(void *data, struct cm_surface_data *surface_data);
 #define B200_CM_SURFACE_QUEUE_SIZE 3
 #define B200_CM_FLAG_CONVERT_RGB 1
 #define B200_CM_FLAG_CONVERT_YUV 2
+#define B200_CM_FLAG_RAW_TEXTURE 4 /* the ROI source's own texture, always set for an ROI (roi.c:35) */
 #define B200_CM_FLAG_ROI 8 /* crop to (x0, y0)-(x1, y1) before staging (common.h:93, common.c:272-282) */
 
 struct b200_cm_queue_item {

@@ -276,6 +276,29 @@ ROI_REGISTER(his)
 ROI_REGISTER(wvs)
 ROI_REGISTER(vss)
 
+static uint32_t convert_flags(uint32_t components)
+{
+	return ((components & SCOPE_COMP_RGB) ? B200_CM_FLAG_CONVERT_RGB : 0u) |
+	       ((components & SCOPE_COMP_YUV) ? B200_CM_FLAG_CONVERT_YUV : 0u);
+}
+
+uint32_t b200_roi_capture_flags(struct b200_roi_source *roi)
+{
+	uint32_t flags = 0;
+	pthread_mutex_lock(&roi->sources_mutex);
+	for (int i = 0; i < roi->n_his; i++)
+		flags |= convert_flags(roi->his[i]->components);
+	for (int i = 0; i < roi->n_wvs; i++)
+		flags |= convert_flags(roi->wvs[i]->components);
+	if (roi->n_vss)
+		flags |= B200_CM_FLAG_CONVERT_YUV;
+	const bool any = roi->n_his || roi->n_wvs || roi->n_vss;
+	pthread_mutex_unlock(&roi->sources_mutex);
+	if (roi->mode == SCOPE_MODE_FUSED)
+		flags = any ? B200_CM_FLAG_CONVERT_RGB : 0u;
+	return flags | B200_CM_FLAG_ROI | B200_CM_FLAG_RAW_TEXTURE;
+}
+
 void b200_roi_surface_cb(void *data, struct cm_surface_data *sd)
 {
 	struct b200_roi_source *roi = data;

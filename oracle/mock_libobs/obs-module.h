@@ -118,3 +118,32 @@ obs_property_t *obs_properties_add_float(obs_properties_t *props, const char *na
 					 double min, double max, double step);
 obs_property_t *obs_properties_add_bool(obs_properties_t *props, const char *name, const char *description);
 obs_property_t *obs_properties_add_color(obs_properties_t *props, const char *name, const char *description);
+
+/* ---- for src/roi.c (ref_harness_roi.c): a working dynamic array, opaque proc-handler types ---- */
+#define DARRAY(type) struct { type *array; size_t num; size_t capacity; }
+#define da_free(v) do { free((v).array); (v).array = NULL; (v).num = (v).capacity = 0; } while (0)
+#define da_push_back(v, item_ptr)                                                          \
+	do {                                                                               \
+		if ((v).num == (v).capacity) {                                             \
+			(v).capacity = (v).capacity ? (v).capacity * 2 : 4;                \
+			(v).array = realloc((v).array, (v).capacity * sizeof(*(v).array)); \
+		}                                                                          \
+		(v).array[(v).num++] = *(item_ptr);                                        \
+	} while (0)
+#define da_erase_item(v, item_ptr)                                                                     \
+	do {                                                                                           \
+		for (size_t i_ = 0; i_ < (v).num; i_++)                                                \
+			if ((v).array[i_] == *(item_ptr)) {                                            \
+				memmove(&(v).array[i_], &(v).array[i_ + 1],                            \
+					((v).num - i_ - 1) * sizeof(*(v).array));                      \
+				(v).num--;                                                             \
+				break;                                                                 \
+			}                                                                              \
+	} while (0)
+typedef struct calldata { void *stack; size_t size; size_t capacity; bool fixed; } calldata_t;
+typedef struct proc_handler proc_handler_t;
+enum { GS_BLEND_ZERO, GS_BLEND_ONE, GS_BLEND_SRCALPHA = 4, GS_BLEND_INVSRCALPHA = 5 };
+enum { OBS_SOURCE_CAP_DISABLED = 1 << 10 };
+proc_handler_t *obs_source_get_proc_handler(const obs_source_t *source);
+obs_source_t *obs_get_source_by_name(const char *name);
+gs_texture_t *gs_texrender_get_texture(const gs_texrender_t *texrender);

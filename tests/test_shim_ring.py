@@ -326,3 +326,131 @@ def test_empty_surfaces_match_the_reference(shim, ref):
                         lib.b200_wvs_destroy(C.byref(wvs))
                         lib.b200_vss_destroy(C.byref(vss))
     assert n_flips > 100
+
+
+def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
+    """The ROI source's host logic against the reference's own src/roi.c (compiled into oracle/_ref with
+    cm_tick / cm_render_target replaced by counters): on which ticks the capture core is ticked and
+    asked to stage (frame interleave, roi.c:266-277, 523-532), how a requested rectangle is clamped
+    (roi_send_range, roi.c:478-500), which planes the registered scopes make it stage (roi.c:533-540)."""
+    lib, L = shim, ref.lib
+    L.ref_roi_new.restype = C.c_void_p
+    L.ref_roi_new.argtypes = [C.c_int]
+    L.ref_roi_free.argtypes = [C.c_void_p]
+    L.ref_roi_tick.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_roi_target_render.argtypes = [C.c_void_p]
+    L.ref_roi_add_consumer.restype = C.c_void_p
+    L.ref_roi_add_consumer.argtypes = [C.c_void_p, C.c_uint32]
+    L.ref_roi_remove_consumer.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_roi_send_range.argtypes = [C.c_int] * 4 + [C.c_uint32] * 2 + [C.c_void_p]
+    lib.b200_roi_target_render.restype = C.c_bool
+    lib.b200_roi_target_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                           C.c_uint32]
+    lib.b200_roi_tick.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_roi_destroy.argtypes = [C.c_void_p]
+    lib.b200_roi_capture_flags.restype = C.c_uint32
+    lib.b200_roi_capture_flags.argtypes = [C.c_void_p]
+    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("his", "wvs", "vss"):
+        getattr(lib, f"b200_roi_register_{n}").argtypes = [C.c_void_p, C.c_void_p]
+
+    class Roi(C.Structure):   # include/cm_shim.h: struct b200_roi_source
+        _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("sources_mutex", C.c_byte * 40),
+                    ("his", C.c_void_p * 8), ("wvs", C.c_void_p * 8), ("vss", C.c_void_p * 8),
+                    ("n_his", C.c_int), ("n_wvs", C.c_int), ("n_vss", C.c_int), ("wave_tmp", C.c_void_p),
+                    ("wave_tmp_width", C.c_uint32), ("n_interleave", C.c_int), ("i_interleave", C.c_int),
+                    ("interleave_rendered", C.c_bool)]
+
+    rendered_off = 3 * 56 + 12       # struct b200_cm_source: `rendered` follows queue[3] and the three indices
+    rng = np.random.default_rng(11)
+
+    # --- pacing: random sequences of ticks with 0..2 renders each ---
+    for n_interleave in (-1, 0, 1, 2, 3, 5):
+        st = L.ref_roi_new(n_interleave)
+        roi = Roi()
+        lib.b200_roi_init(C.byref(roi), None, 1)
+        roi.n_interleave = n_interleave
+        cm = C.create_string_buffer(4096)
+        lib.b200_cm_create(cm)
+        flag = C.c_bool.from_buffer(cm, rendered_off)
+        ticks = renders = 0
+        for frame in range(60):
+            flag.value = True                              # cm_tick resets it (common.c:216-221)
+            lib.b200_roi_tick(C.byref(roi), cm)
+            ticks += not flag.value
+            assert L.ref_roi_tick(st, None) == ticks, (n_interleave, frame)
+            for _ in range(int(rng.integers(0, 3))):
+                flag.value = False                         # cm_render_target sets it (common.c:225-227)
+                got = lib.b200_roi_target_render(C.byref(roi), cm, None, None, 0, 0, 0)
+                renders += flag.value
+                want = L.ref_roi_target_render(st)
+                assert (bool(want >> 16), want & 0xFFFF) == (got, renders), (n_interleave, frame)
+        assert ticks > 0 and renders > 0
+        lib.b200_cm_destroy(cm)
+        lib.b200_roi_destroy(C.byref(roi))
+        L.ref_roi_free(st)
+
+    # --- clamping of the requested rectangle ---
+    out = (C.c_int * 4)()
+
+    class CmTail(C.Structure):   # the last fields of struct b200_cm_source
+        _fields_ = [("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong), ("x0", C.c_int), ("x1", C.c_int),
+                    ("y0", C.c_int), ("y1", C.c_int)]
+
+    tail_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16 + 8     # flags_off (see above) + flags + colorspace
+    for _ in range(300):
+        w, h = int(rng.integers(1, 5000)), int(rng.integers(1, 3000))
+        r = [int(v) for v in rng.integers(-50, 5200, 4)]
+        if rng.random() < 0.3:
+            r[int(rng.integers(0, 4))] = -1
+        cm = C.create_string_buffer(4096)
+        lib.b200_cm_create(cm)
+        lib.b200_cm_set_roi(cm, r[0], r[1], r[2], r[3], w, h)
+        L.ref_roi_send_range(r[0], r[1], r[2], r[3], w, h, out)
+        t = CmTail.from_buffer(cm, tail_off)
+        assert (t.x0, t.y0, t.x1, t.y1) == tuple(out), (r, w, h)
+        lib.b200_cm_destroy(cm)
+
+    # --- capture flags from the registered scopes (surface mode = the reference's rule) ---
+    def ref_flags(comps_his, comps_wvs, n_vss):
+        st = L.ref_roi_new(1)
+        cons = [L.ref_roi_add_consumer(st, (1 if c & 0x07 else 0) | (2 if c & 0x70 else 0)) for c in comps_his + comps_wvs]
+        cons += [L.ref_roi_add_consumer(st, 2) for _ in range(n_vss)]
+        f = C.c_uint32(0)
+        L.ref_roi_tick(st, C.byref(f))
+        for c in cons:
+            L.ref_roi_remove_consumer(st, c)
+        L.ref_roi_free(st)
+        return f.value
+
+    for comps_his, comps_wvs, n_vss in (([], [], 0), ([0x07], [], 0), ([0x20], [0x07], 0), ([], [0x70], 0), ([], [], 1),
+                                        ([0x07], [0x07], 1), ([0x50, 0x07], [0x20], 2), ([0x00], [], 0)):
+        for mode in (1, 0):    # SCOPE_MODE_SURFACE, SCOPE_MODE_FUSED
+            roi = Roi()
+            lib.b200_roi_init(C.byref(roi), None, mode)
+            keep = []
+            for c in comps_his:
+                s = C.create_string_buffer(256)
+                lib.b200_his_init(s, None, c)
+                lib.b200_roi_register_his(C.byref(roi), s)
+                keep.append(s)
+            for c in comps_wvs:
+                s = C.create_string_buffer(256)
+                lib.b200_wvs_init(s, None, c)
+                lib.b200_roi_register_wvs(C.byref(roi), s)
+                keep.append(s)
+            for _ in range(n_vss):
+                s = C.create_string_buffer(256)
+                lib.b200_vss_init(s, None)
+                lib.b200_roi_register_vss(C.byref(roi), s)
+                keep.append(s)
+            got = lib.b200_roi_capture_flags(C.byref(roi))
+            if mode == 1:
+                assert got == ref_flags(comps_his, comps_wvs, n_vss), (comps_his, comps_wvs, n_vss)
+            else:
+                assert got == (8 | 4 | (1 if keep else 0))
+            lib.b200_roi_destroy(C.byref(roi))
