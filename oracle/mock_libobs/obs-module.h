@@ -147,3 +147,23 @@ enum { OBS_SOURCE_CAP_DISABLED = 1 << 10 };
 proc_handler_t *obs_source_get_proc_handler(const obs_source_t *source);
 obs_source_t *obs_get_source_by_name(const char *name);
 gs_texture_t *gs_texrender_get_texture(const gs_texrender_t *texrender);
+
+/* ---- for src/common.c (ref_harness_common.c; the functions themselves are FAKES defined there) ---- */
+enum { GS_BGRA = 4 };
+enum { GS_ZS_NONE = 0 };
+enum { GS_CLEAR_COLOR = 1 };
+struct obs_video_info { uint32_t base_width, base_height; int colorspace; };
+static inline void vec4_zero(struct vec4 *v) { v->x = v->y = v->z = v->w = 0.0f; }
+char *bstrdup(const char *str);
+obs_source_t *obs_weak_source_get_source(obs_weak_source_t *weak);
+obs_weak_source_t *obs_source_get_weak_source(obs_source_t *source);
+obs_source_t *obs_get_output_source(uint32_t channel);
+obs_source_t *obs_frontend_get_current_preview_scene(void);
+bool obs_source_removed(const obs_source_t *source);
+uint32_t obs_source_get_width(obs_source_t *source);
+uint32_t obs_source_get_height(obs_source_t *source);
+bool obs_get_video_info(struct obs_video_info *ovi);
+gs_texrender_t *gs_texrender_create(int format, int zsformat);
+bool gs_texrender_begin(gs_texrender_t *texrender, uint32_t cx, uint32_t cy);
+gs_stagesurf_t *gs_stagesurface_create(uint32_t width, uint32_t height, int color_format);
+bool gs_stagesurface_map(gs_stagesurf_t *stagesurf, uint8_t **data, uint32_t *linesize);

@@ -454,3 +454,129 @@ def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
             else:
                 assert got == (8 | 4 | (1 if keep else 0))
             lib.b200_roi_destroy(C.byref(roi))
+
+
+class _CmItem(C.Structure):   # include/cm_shim.h: struct b200_cm_queue_item
+    _fields_ = [("staged", C.c_void_p), ("staged_bytes", C.c_size_t), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("linesize", C.c_uint32), ("flags", C.c_uint32),
+                ("colorspace", C.c_int), ("cb", C.c_void_p), ("cb_data", C.c_void_p)]
+
+
+class _Cm(C.Structure):       # include/cm_shim.h: struct b200_cm_source
+    _fields_ = [("queue", _CmItem * 3), ("i_write_queue", C.c_int), ("i_staging_queue", C.c_int),
+                ("i_read_queue", C.c_int), ("rendered", C.c_bool), ("pipeline_thread", C.c_ulong),
+                ("pipeline_mutex", C.c_byte * 40), ("pipeline_cond", C.c_byte * 48),
+                ("pipeline_thread_running", C.c_bool), ("request_exit", C.c_bool), ("worker_busy", C.c_bool),
+                ("callback", C.c_void_p), ("callback_data", C.c_void_p), ("flags", C.c_uint32),
+                ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong),
+                ("x0", C.c_int), ("x1", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
+
+
+@pytest.mark.parametrize("flags,roi", [(1, None), (3, None), (2, None), (3, (5, 3, 29, 17)), (1, (0, 0, 40, 9))])
+def test_capture_core_matches_the_reference(shim, pkg, flags, roi):
+    """b200_cm_* against the reference's own capture core: src/common.c compiled unmodified on a software
+    graphics layer (oracle/_ref/libref_common.so; the YUV shader is a stand-in that inverts B, G, R).
+    Same schedule on both sides - ticks, renders, a worker that is sometimes held inside the callback -
+    and the same things must come out: which renders stage a slot and which are dropped, the queue
+    indices after every step, and every surface the callback sees (size, pitch, planes, bytes)."""
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_common.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_common.so not built (needs /root/reference at build time)")
+    R, lib = C.CDLL(so), shim
+    R.refc_new.restype = C.c_void_p
+    R.refc_new.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, CB, C.c_void_p]
+    for n in ("refc_free", "refc_tick", "refc_idle"):
+        getattr(R, n).argtypes = [C.c_void_p]
+    R.refc_render.argtypes = [C.c_void_p, C.c_void_p]
+    R.refc_indices.argtypes = [C.c_void_p, C.c_void_p]
+    R.refc_set_roi.argtypes = [C.c_void_p] + [C.c_int] * 4
+    R.refc_callbacks.restype = C.c_long
+    R.refc_callbacks.argtypes = [C.c_void_p]
+    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+
+    W, H = 40, 24
+    gate = threading.Event()
+    gate.set()
+    seen = {"ref": [], "shim": []}
+    inside = {"ref": 0, "shim": 0}
+
+    def make_cb(who):
+        def cb(_d, sd):
+            inside[who] = 1
+            gate.wait()
+            s = sd.contents
+            n = s.linesize * s.height
+            planes = tuple(None if not p else bytes(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (n,))
+                                                    .reshape(s.height, s.linesize)[:, :s.width * 4])
+                           for p in (s.rgb_data, s.yuv_data))
+            seen[who].append((s.width, s.height, s.colorspace, planes))
+            inside[who] = 0
+        return CB(cb)
+
+    cb_ref, cb_shim = make_cb("ref"), make_cb("shim")
+    ref = R.refc_new(flags, 1, W, H, cb_ref, None)
+    cm = _Cm()
+    lib.b200_cm_create(C.byref(cm))
+    cm.flags, cm.colorspace = flags, 1
+    lib.b200_cm_request(C.byref(cm), cb_shim, None)
+    if roi:
+        R.refc_set_roi(ref, *roi)
+        lib.b200_cm_set_roi(C.byref(cm), roi[0], roi[1], roi[2], roi[3], W, H)
+
+    def ref_settled():
+        return inside["ref"] or R.refc_idle(ref)
+
+    def shim_settled():
+        nxt = (cm.i_read_queue + 1) % 3
+        return inside["shim"] or ((cm.i_write_queue == nxt or cm.i_staging_queue == nxt) and not cm.worker_busy)
+
+    def settle():
+        for who in (ref_settled, shim_settled):
+            ok = 0
+            for _ in range(4000):            # the worker is either waiting for work or inside the callback
+                ok = ok + 1 if who() else 0
+                if ok >= 3:
+                    break
+                time.sleep(0.0005)
+            assert ok >= 3, "worker did not settle"
+
+    rng = np.random.default_rng(flags * 7 + (1 if roi else 0))
+    frames = []
+    trace = []
+    for step in range(40):
+        if step in (12, 26):
+            gate.clear()                      # hold the worker inside the next callback for a while
+        if step in (19, 33):
+            gate.set()
+            settle()
+        f = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        yuv = f.copy()
+        yuv[..., :3] = 255 - f[..., :3]       # what the stand-in shader of the harness writes
+        yuv[..., 3] = 255
+        frames.append((f, yuv))               # keep alive while staged
+        R.refc_tick(ref)
+        lib.b200_cm_tick(C.byref(cm))
+        n_render = 2 if step % 5 == 0 else 1  # a second render in the same tick is ignored (common.c:225-227)
+        for _ in range(n_render):
+            a = bool(R.refc_render(ref, f.ctypes.data))
+            b = bool(lib.b200_cm_render_target(C.byref(cm), f.ctypes.data, yuv.ctypes.data, W * 4, W, H))
+            settle()
+            idx = (C.c_int * 3)()
+            R.refc_indices(ref, idx)
+            trace.append((step, a, b, tuple(idx), (cm.i_write_queue, cm.i_staging_queue, cm.i_read_queue)))
+    gate.set()
+    settle()
+    for step, a, b, ia, ib in trace:
+        assert a == b and ia == ib, (step, a, b, ia, ib)
+    assert any(not a for _, a, *_ in trace) and sum(a for _, a, *_ in trace) > 15   # drops happened, and stages
+    assert len(seen["ref"]) == len(seen["shim"]) > 10
+    for i, (x, y) in enumerate(zip(seen["ref"], seen["shim"])):
+        assert x[:3] == y[:3], (i, x[:3], y[:3])
+        assert x[3] == y[3], f"surface {i}: plane bytes differ"
+    want_planes = (bool(flags & 1), bool(flags & 2))
+    assert all((p[3][0] is not None, p[3][1] is not None) == want_planes for p in seen["shim"])
+    if roi:
+        assert seen["shim"][0][:2] == (roi[2] - roi[0], roi[3] - roi[1])
+    lib.b200_cm_destroy(C.byref(cm))
+    R.refc_free(ref)
