@@ -179,3 +179,40 @@ def test_oracle_matches_reference_loops_random_geometry(oracle, ref):
         assert np.array_equal(oracle.vectorscope(yuv, width=w), ref.vectorscope(yuv, width=w))
 
     check()
+
+
+def test_transform_coefficients_are_the_effect_files(oracle):
+    """The 18 coefficients of data/common.effect:23-43, read from the reference's file itself (build container
+    only), are the ones the product multiplies by (coef_for in csrc/scope_ffi.cu, as integers x 10^6) and the ones
+    the oracle's table is made from (checked through the table: one channel at a time, two colours each)."""
+    import re
+    effect = "/root/reference/data/common.effect"
+    if not os.path.exists(effect):
+        pytest.skip("reference tree not present")
+    text = open(effect).read()
+    got = {}
+    for cs, name in ((1, "PSConvertRGB_YUV601"), (2, "PSConvertRGB_YUV709")):
+        body = text[text.index(name):]
+        body = body[:body.index("return")]
+        rows = {}
+        for comp, ch in (("z", "u"), ("y", "y"), ("x", "v")):     # uv00.z = U, .y = Y, .x = V
+            m = re.search(r"uv00\." + comp + r"\s*=\s*([+-][0-9.]+)\s*\*\s*rgb\.x\s*([+-][0-9.]+)\s*\*\s*rgb\.y\s*"
+                          r"([+-][0-9.]+)\s*\*\s*rgb\.z([^;]*);", body)
+            rows[ch] = ([m.group(i) for i in (1, 2, 3)], m.group(4).replace(" ", ""))
+        assert rows["u"][1] == "+0.5-1.0/256.0" and rows["y"][1] == "" and rows["v"][1] == "+0.5"
+        got[cs] = [[round(float(c) * 10 ** 6) for c in rows[ch][0]] for ch in "uyv"]
+        assert all(len(c.split(".")[1]) == 6 for ch in "uyv" for c in rows[ch][0]), "six decimals: S is an integer"
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "obs-color-monitor_b200", "csrc",
+                            "scope_ffi.cu")).read()
+    for cs, tag in ((1, "k601"), (2, "k709")):
+        m = re.search(tag + r"\[3\]\[3\]\s*=\s*\{(.*?)\};", src, re.S)
+        product = [int(v) for v in re.findall(r"[+-]?\d+", m.group(1))]
+        assert product == [c for row in got[cs] for c in row], tag
+    for cs in (1, 2):
+        tab = oracle.rgb_to_yuv_table(cs)[0]
+        off = (127003906, 500000, 128000000)          # floor(10^6 (255 off + 1/2)), DESIGN.md section 3
+        for rgb in ((255, 0, 0), (0, 255, 0), (0, 0, 255), (13, 200, 77)):
+            word = int(tab[rgb[0] << 16 | rgb[1] << 8 | rgb[2]])
+            for ch in range(3):
+                s = sum(c * v for c, v in zip(got[cs][ch], rgb)) + off[ch]
+                assert (word >> (8 * ch)) & 0xFF == s // 10 ** 6
