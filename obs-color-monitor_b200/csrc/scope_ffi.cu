@@ -96,32 +96,6 @@ int fail(scope_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess
 			return fail(ctx, SCOPE_ERR_CUDA, #call, e_);   \
 	} while (0)
 
-// 10^6 x the coefficients printed in data/common.effect:27-29 (BT.601) and :38-40 (BT.709), as
-// integers, order R, G, B; K = floor(10^6 * (255 * off + 1/2)) with off = 1/2 - 1/256 (U), 0 (Y),
-// 1/2 (V).  The kernel multiplies carriers (kCarrierBias + byte), so the bias they add is taken out
-// of K here (mod 2^32; the bias is 0 in SCOPE_FADDR builds).
-Coef coef_for(int colorspace)
-{
-	static const int32_t k601[3][3] = {{-147643, -289855, +437500}, {+299000, +587000, +114000},
-					   {+437500, -366351, -71147}};
-	static const int32_t k709[3][3] = {{-100643, -338571, +439216}, {+212600, +715200, +72200},
-					   {+439216, -398941, -40273}};
-	static const uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
-	const int32_t(*m)[3] = colorspace == 1 ? k601 : k709;
-	Coef c;
-	uint32_t *rows[3] = {c.u, c.y, c.v};
-	uint32_t *adds[3] = {&c.ku, &c.ky, &c.kv};
-	for (int ch = 0; ch < 3; ch++) {
-		uint32_t sum = 0;
-		for (int i = 0; i < 3; i++) {
-			rows[ch][i] = (uint32_t)m[ch][i];
-			sum += (uint32_t)m[ch][i];
-		}
-		*adds[ch] = k_add[ch] - sum * kCarrierBias;
-	}
-	return c;
-}
-
 // components -> (source plane, channel mask) exactly like histogram.c:367-377 / waveform.c:228-238
 void decode_components(uint32_t comp, int &src, uint32_t &mask)
 {

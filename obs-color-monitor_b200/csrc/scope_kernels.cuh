@@ -20,8 +20,16 @@
 // instruction in the steady-state loop of tma_consume counts.
 #pragma once
 #include <cstdint>
+// SCOPE_EMULATE: this file compiled for the HOST on top of tools/simt/cuda_emul.h (every CUDA thread a
+// coroutine; tests/test_kernel_emulation.py checks the kernels' logic against the oracle without a GPU).
+// The product never defines it; each PTX helper below has its emulated twin next to it.
+#ifndef SCOPE_EMULATE
 #include <cuda.h>
 #include <cuda_runtime.h>
+#define SCOPE_DYNAMIC_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#else
+#define SCOPE_DYNAMIC_SMEM(name) uint8_t *name = emul::W->cur->cta->smem.data()
+#endif
 
 namespace scope {
 
@@ -156,23 +164,42 @@ struct StripParams {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
+#ifdef SCOPE_EMULATE
+	return emul::kSmemBase + (uint32_t)(static_cast<const uint8_t *>(p) - emul::W->cur->cta->smem.data());
+#else
 	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+#endif
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
+#ifdef SCOPE_EMULATE
+	return emul::mbar_init(bar, count);
+#else
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
+#ifdef SCOPE_EMULATE
+	return emul::mbar_expect_tx(bar, bytes);
+#else
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
+#ifdef SCOPE_EMULATE
+	return emul::mbar_arrive(bar);
+#else
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+#ifdef SCOPE_EMULATE
+	return emul::mbar_wait(bar, parity);
+#else
 	asm volatile("{\n"
 		     ".reg .pred p;\n"
 		     "WAIT_%=:\n"
@@ -183,10 +210,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 		     "}" ::"r"(bar),
 		     "r"(parity)
 		     : "memory");
+#endif
 }
 // non-blocking: has the phase with this parity completed?  (acquire, like try_wait)
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
 {
+#ifdef SCOPE_EMULATE
+	return emul::mbar_test(bar, parity) ? 1u : 0u;
+#else
 	uint32_t ok;
 	asm volatile("{\n"
 		     ".reg .pred p;\n"
@@ -197,25 +228,38 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
 		     : "r"(bar), "r"(parity)
 		     : "memory");
 	return ok;
+#endif
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z)
 {
+#ifdef SCOPE_EMULATE
+	return emul::tma_issue(dst, map, bar, x, y, z);
+#else
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
 		     " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
 		     "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
 		     : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t val)
 {
+#ifdef SCOPE_EMULATE
+	return atomicAdd(reinterpret_cast<uint32_t *>(emul::smem_ptr(addr)), val);
+#else
 	uint32_t old;
 	asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(val));
 	return old;
+#endif
 }
 __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
 {
+#ifdef SCOPE_EMULATE
+	return *static_cast<const uint32_t *>(p);
+#else
 	uint32_t v;
 	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
+#endif
 }
 
 // N consecutive 128-byte tile rows -> one pixel per lane per row, i.e. exactly what
@@ -227,6 +271,21 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void *p)
 template <int N>
 __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t (&p)[N])
 {
+#ifdef SCOPE_EMULATE
+	for (int k = 0; k + 3 < N; k += 4) {
+		uint32_t r[4];
+		emul::ldmatrix<4>(rows_addr + (uint32_t)k * 128u + (uint32_t)lane * 16u, r);
+		for (int j = 0; j < 4; j++)
+			p[k + j] = r[j];
+	}
+	if (N % 4 == 2) {
+		uint32_t r[2];
+		emul::ldmatrix<2>(rows_addr + (uint32_t)(N - 2) * 128u + (uint32_t)(lane & 15) * 16u, r);
+		p[N - 2] = r[0];
+		p[N - 1] = r[1];
+	}
+	return;
+#else
 	// (callers only come here with N even: groups of four rows, then one pair if N % 4 == 2)
 #pragma unroll
 	for (int k = 0; k + 3 < N; k += 4)
@@ -239,6 +298,7 @@ __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t
 			     : "=r"(p[N - 2]), "=r"(p[N - 1])
 			     : "r"(rows_addr + (uint32_t)(N - 2) * 128u + (uint32_t)(lane & 15) * 16u)
 			     : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -256,17 +316,75 @@ __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t
 // instead of the half-rate FMA-heavy (IMAD) or ALU (LEA) pipes that bound the inner loop.
 constexpr uint32_t kCarrierBias = SCOPE_FADDR ? 0u : 0x4B000000u;
 
+// (host side)
+// 10^6 x the coefficients printed in data/common.effect:27-29 (BT.601) and :38-40 (BT.709), as
+// integers, order R, G, B; K = floor(10^6 * (255 * off + 1/2)) with off = 1/2 - 1/256 (U), 0 (Y),
+// 1/2 (V).  The kernel multiplies carriers (kCarrierBias + byte), so the bias they add is taken out
+// of K here (mod 2^32; the bias is 0 in SCOPE_FADDR builds).
+inline Coef coef_for(int colorspace)
+{
+	static const int32_t k601[3][3] = {{-147643, -289855, +437500}, {+299000, +587000, +114000},
+					   {+437500, -366351, -71147}};
+	static const int32_t k709[3][3] = {{-100643, -338571, +439216}, {+212600, +715200, +72200},
+					   {+439216, -398941, -40273}};
+	static const uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
+	const int32_t(*m)[3] = colorspace == 1 ? k601 : k709;
+	Coef c;
+	uint32_t *rows[3] = {c.u, c.y, c.v};
+	uint32_t *adds[3] = {&c.ku, &c.ky, &c.kv};
+	for (int ch = 0; ch < 3; ch++) {
+		uint32_t sum = 0;
+		for (int i = 0; i < 3; i++) {
+			rows[ch][i] = (uint32_t)m[ch][i];
+			sum += (uint32_t)m[ch][i];
+		}
+		*adds[ch] = k_add[ch] - sum * kCarrierBias;
+	}
+	return c;
+}
+
+
 // a * b + c on the bit patterns of small non-negative integers (all < 2^23), b a float constant
 __device__ __forceinline__ uint32_t fma_bits(uint32_t a, float b, uint32_t c)
 {
+#ifdef SCOPE_EMULATE
+	return emul::fma_bits(a, b, c);
+#else
 	float d;
 	asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(__uint_as_float(a)), "f"(b), "f"(__uint_as_float(c)));
 	return __float_as_uint(d);
+#endif
+}
+
+// constants the compiler must not see through: the carrier bias stays in a register so that PRMT can take
+// its selector as the immediate; the zero is used to build data dependencies
+__device__ __forceinline__ uint32_t opaque_carrier_bias()
+{
+#ifdef SCOPE_EMULATE
+	return kCarrierBias;
+#else
+	uint32_t v;
+	asm volatile("mov.u32 %0, %1;" : "=r"(v) : "n"(kCarrierBias));
+	return v;
+#endif
+}
+__device__ __forceinline__ uint32_t opaque_zero()
+{
+#ifdef SCOPE_EMULATE
+	return 0u;
+#else
+	uint32_t v;
+	asm volatile("mov.u32 %0, 0;" : "=r"(v));
+	return v;
+#endif
 }
 
 template <int K>
 __device__ __forceinline__ uint32_t carrier(uint32_t pixel, uint32_t magic)
 {
+#ifdef SCOPE_EMULATE
+	return emul::prmt(pixel, magic, 0x7650u + (uint32_t)K);
+#else
 	uint32_t r;
 	if (K == 0)
 		asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(pixel), "r"(magic));
@@ -275,6 +393,7 @@ __device__ __forceinline__ uint32_t carrier(uint32_t pixel, uint32_t magic)
 	else
 		asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(pixel), "r"(magic));
 	return r;
+#endif
 }
 
 // RGB -> YUV (data/common.effect:23-43), pinned as the EXACT value of the shader's expression
@@ -358,7 +477,12 @@ struct SmemLayout {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void red_shared(uint32_t addr, uint32_t val)
 {
+#ifdef SCOPE_EMULATE
+	atomicAdd(reinterpret_cast<uint32_t *>(emul::smem_ptr(addr)), val);
+	return;
+#else
 	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val));
+#endif
 }
 
 // Waveform / histogram column bins: plane0[level][lane] = (count B|U : lo16, count G|Y : hi16),
@@ -590,7 +714,11 @@ __device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef,
 template <int NW>
 __device__ __forceinline__ void workers_bar()
 {
+#ifdef SCOPE_EMULATE
+	return emul::bar_sync(1, NW * 32);
+#else
 	asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+#endif
 }
 
 template <int NW>
@@ -1030,12 +1158,12 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic; // 0x4B000000 kept in a register so PRMT can take the selector as its immediate
-	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	magic = opaque_carrier_bias();
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
 			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
 	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
-	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+	zero = opaque_zero();
 	uint32_t stage = 0, phase = 0, qr = 0;
 	uint32_t cur_frame = 0xFFFFFFFFu;
 
@@ -1242,7 +1370,9 @@ __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint
 			mbar_init(bar_full + 8 * s, 1);
 			mbar_init(bar_empty + 8 * s, EMPTY_ARRIVALS);
 		}
+#ifndef SCOPE_EMULATE
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
 	}
 	__syncthreads();
 }
@@ -1263,7 +1393,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, 
 {
 	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
 	constexpr int NW = kTmaWarps, RPW = kTileRows / NW;
-	extern __shared__ __align__(128) uint8_t smem[];
+	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);
 	const uint32_t bar_full = smem_base + L::kBarOff;
@@ -1310,12 +1440,12 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 	const uint32_t groups_inside = P.height / N;  // groups [0, groups_inside) have all 4 rows in the frame
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic;
-	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	magic = opaque_carrier_bias();
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
 			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
 	uint32_t zero;
-	asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+	zero = opaque_zero();
 	uint32_t tile_seq = 0;  // tiles this CTA consumed before the current strip (same in every warp)
 	// Barrier discipline.  An mbarrier wait names a phase by its parity only, so a waiter must be
 	// neither two phases ahead of the barrier nor two behind.  Every warp therefore visits EVERY
@@ -1485,7 +1615,7 @@ __global__ void __launch_bounds__(kGroupWarps * 32 + 32, 1)
 {
 	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
 	constexpr int NW = kGroupWarps;
-	extern __shared__ __align__(128) uint8_t smem[];
+	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);
 	const uint32_t bar_full = smem_base + L::kBarOff;
@@ -1518,7 +1648,7 @@ __global__ void __launch_bounds__((kSplitVsWarps + kSplitBinWarps) * 32 + 32, 1)
 	using L = SmemLayout<SRC_RGB, true, SURFACE, true>;
 	constexpr int NV = kSplitVsWarps, NB = kSplitBinWarps, NW = NV + NB;
 	constexpr int RV = kTileRows / NV, RB = kTileRows / NB;
-	extern __shared__ __align__(128) uint8_t smem[];
+	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);
 	const uint32_t bar_full = smem_base + L::kBarOff;
@@ -1550,7 +1680,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 {
 	using L = SmemLayout<SRC, VSCOPE, SURFACE, false>;
 	constexpr int NW = kLdgWarps, RPW = kLdgRows;
-	extern __shared__ __align__(128) uint8_t smem[];
+	SCOPE_DYNAMIC_SMEM(smem);
 	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
 	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
 	const uint32_t smem_base = smem_u32(smem);
@@ -1566,7 +1696,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic;
-	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	magic = opaque_carrier_bias();
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
 			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
 	const Coef coef = P.coef;
@@ -1612,6 +1742,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 		flush_vscope<NW>(P, vs, cur_frame, tid);
 }
 
+#ifndef SCOPE_EMULATE
 // ---------------------------------------------------------------------------
 // finalize kernels
 // ---------------------------------------------------------------------------
@@ -1705,7 +1836,7 @@ __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out
 	const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 2;
 	// index r<<16|g<<8|b is already the little-endian BGRA word b | g<<8 | r<<16
 	uint32_t magic;
-	asm volatile("mov.u32 %0, %1;" : "=r"(magic) : "n"(kCarrierBias));
+	magic = opaque_carrier_bias();
 #pragma unroll
 	for (uint32_t j = i; j < i + 2; j++) {
 		const uint32_t bgr[3] = {carrier<0>(j, magic), carrier<1>(j, magic), carrier<2>(j, magic)};
@@ -1714,5 +1845,7 @@ __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out
 		out[j] = __byte_perm(__byte_perm(hi[0], hi[1], 0x3362), hi[2], 0x3610);
 	}
 }
+
+#endif // !SCOPE_EMULATE
 
 } // namespace scope

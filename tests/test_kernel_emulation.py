@@ -1,0 +1,166 @@
+"""The strip kernels' LOGIC without a GPU: csrc/scope_kernels.cuh compiled for the host on a small SIMT emulator
+(tools/simt: every CUDA thread a coroutine under a seeded random scheduler; warp collectives, named barriers,
+mbarriers with transaction counts, TMA tile loads that land late and out of order, ldmatrix, the PTX arithmetic
+helpers) and compared bit for bit with the CPU oracle.  It covers what the GPU tests cover - but also the
+build-flag variants prepared for the next round, which have not run on a GPU yet, and
+it explores far more interleavings than the hardware does.  Timing and bank conflicts are not modelled."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tools", "simt", "_build")
+SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
+          [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", "scope_kernels.cuh")]
+VARIANTS = ["default", "w8", "w12n6", "w12n8", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
+K_TMA, K_LDG, K_GROUP = 0, 1, 2
+
+
+class Request(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("yuv", C.c_void_p), ("linesize", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("n_frames", C.c_uint32), ("frame_stride", C.c_uint64),
+                ("colorspace", C.c_int32), ("surface", C.c_int32), ("src", C.c_int32), ("vscope", C.c_int32),
+                ("bins_mask", C.c_uint32), ("hist_mask", C.c_uint32), ("wave_mask", C.c_uint32),
+                ("hist", C.c_void_p), ("wave", C.c_void_p), ("vs_acc", C.c_void_p), ("wave_pairs", C.c_void_p),
+                ("out_width", C.c_uint32), ("x_offset", C.c_uint32), ("partial", C.c_uint32),
+                ("kernel", C.c_int32), ("ctas", C.c_int32), ("seed", C.c_uint32), ("tma_land_percent", C.c_int32),
+                ("steps", C.c_int64), ("error", C.c_char * 256)]
+
+
+@pytest.fixture(scope="session")
+def emul_libs():
+    newest = max(os.path.getmtime(f) for f in SOURCES)
+    paths = {v: os.path.join(BUILD, f"libscope_emul_{v}.so") for v in VARIANTS}
+    if not all(os.path.exists(p) and os.path.getmtime(p) >= newest for p in paths.values()):
+        subprocess.run(["bash", os.path.join(ROOT, "tools", "simt", "build.sh")], check=True)
+    libs = {}
+    for v, p in paths.items():
+        lib = C.CDLL(p)
+        lib.emul_run.argtypes = [C.POINTER(Request)]
+        lib.emul_build_flags.restype = C.c_char_p
+        libs[v] = lib
+    return libs
+
+
+def masks(comp):
+    src = SRC_RGB if comp & 0x07 else (SRC_YUV if comp & 0x70 else SRC_NONE)
+    m = (1 if comp & 0x11 else 0) | (2 if comp & 0x22 else 0) | (4 if comp & 0x44 else 0)
+    return src, (m if src != SRC_NONE else 0)
+
+
+def run(lib, frames, yuv=None, surface=False, hist_comp=0x07, wave_comp=0x07, vscope=True, kernel=K_TMA, ctas=2,
+        seed=1, colorspace=2, land=30):
+    """frames: (n, H, W, 4) u8.  hist_comp and wave_comp must select the same plane (one launch)."""
+    frames = np.ascontiguousarray(frames)
+    n, h, w, _ = frames.shape
+    hsrc, hmask = masks(hist_comp)
+    wsrc, wmask = masks(wave_comp)
+    src = hsrc if hsrc != SRC_NONE else wsrc
+    assert wsrc in (SRC_NONE, src)
+    hist = np.zeros((n, 1024), np.uint32)
+    wave = np.full((n, 256, w, 4), 0xEE, np.uint8)      # the kernel must write every row it owns
+    acc = np.zeros((n, 65536), np.uint32)
+    rq = Request()
+    rq.rgb = frames.ctypes.data
+    rq.yuv = yuv.ctypes.data if yuv is not None else None
+    rq.linesize, rq.width, rq.height, rq.n_frames, rq.frame_stride = w * 4, w, h, n, w * h * 4
+    rq.colorspace, rq.surface, rq.src, rq.vscope = colorspace, int(surface), src, int(vscope)
+    rq.bins_mask, rq.hist_mask, rq.wave_mask = hmask | wmask, hmask, wmask
+    rq.hist, rq.wave, rq.vs_acc = hist.ctypes.data, wave.ctypes.data, acc.ctypes.data
+    rq.out_width, rq.x_offset, rq.partial = w, 0, 0
+    rq.kernel, rq.ctas, rq.seed, rq.tma_land_percent = kernel, ctas, seed, land
+    rc = lib.emul_run(C.byref(rq))
+    assert rc == 0, rq.error.decode()
+    if src == SRC_NONE or not wmask:
+        wave = None
+    return hist, wave, np.minimum(acc, 255).astype(np.uint8).reshape(n, 256, 256), rq.steps
+
+
+def check(oracle, frames, out, yuv_planes, hist_comp, wave_comp, vscope, what):
+    hist, wave, vs, _ = out
+    for i in range(frames.shape[0]):
+        f, y = frames[i], yuv_planes[i]
+        if masks(hist_comp)[1]:
+            assert np.array_equal(hist[i], oracle.histogram_counts(hist_comp, f, y)), f"{what}: histogram, frame {i}"
+        if wave is not None:
+            exp = oracle.waveform(wave_comp, f, y)
+            assert np.array_equal(wave[i][..., :3], exp[..., :3]) and not wave[i][..., 3].any(), f"{what}: waveform, frame {i}"
+        if vscope:
+            assert np.array_equal(vs[i], oracle.vectorscope(y)), f"{what}: vectorscope, frame {i}"
+
+
+def small_batch(pkg):
+    fr = pkg.frames
+    w, h = 70, 150                      # 3 strips (the last one 6 pixels wide), 2 full tiles + a partial one
+    return np.stack([fr.random(w, h, 3), fr.natural(w, h, 4), fr.alpha_stripes(w, h, 5), fr.ramp(w, h)])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fused_all_scopes_every_variant(emul_libs, oracle, pkg, variant):
+    """the headline combination (RGB column bins + vectorscope, transform in registers) on 4 frames x 3 strips,
+    two CTAs sharing the work through the chunk counter, for every build variant"""
+    lib = emul_libs[variant]
+    frames = small_batch(pkg)
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    for seed, land in ((1, 30), (2, 3)):
+        out = run(lib, frames, seed=seed, land=land)
+        check(oracle, frames, out, yuv, 0x07, 0x07, True, f"{variant} ({lib.emul_build_flags().decode()}) seed {seed}")
+
+
+@pytest.mark.parametrize("variant", ["default", "w8_straight", "w12n6"])
+def test_other_kernels_and_modes(emul_libs, oracle, pkg, variant):
+    lib = emul_libs[variant]
+    fr = pkg.frames
+    frames = np.stack([fr.alpha_stripes(45, 131, 7), fr.natural(45, 131, 8)])
+    yuv = [oracle.rgb_to_yuv(f, 1) for f in frames]
+    yuv_arr = np.ascontiguousarray(np.stack(yuv))
+    surface_ok = variant == "default"   # the _x builds' two-plane ring does not fit (SCOPE_EXPERIMENT)
+    cases = [dict(hist_comp=0x70, wave_comp=0x20, vscope=True),                    # fused, YUV bins + vectorscope
+             dict(hist_comp=0x07, wave_comp=0x05, vscope=False),                   # no vectorscope: 2 CTAs per SM kernel
+             dict(hist_comp=0x00, wave_comp=0x00, vscope=True),                    # vectorscope only
+             dict(hist_comp=0x50, wave_comp=0x00, vscope=False)]                   # histogram only, two channels
+    for kw in cases:
+        for kernel in (K_TMA, K_LDG) + ((K_GROUP,) if variant == "default" else ()):
+            out = run(lib, frames, colorspace=1, kernel=kernel, ctas=3, seed=5, **kw)
+            check(oracle, frames, out, yuv, kw["hist_comp"], kw["wave_comp"], kw["vscope"], f"{variant} fused {kw} kernel {kernel}")
+    if surface_ok:
+        rng = np.random.default_rng(3)
+        any_yuv = rng.integers(0, 256, yuv_arr.shape, dtype=np.uint8)      # surface mode takes the plane as it is
+        for kw in (dict(hist_comp=0x07, wave_comp=0x07, vscope=True), dict(hist_comp=0x70, wave_comp=0x70, vscope=True),
+                   dict(hist_comp=0x20, wave_comp=0x50, vscope=False)):
+            for kernel in (K_TMA, K_LDG):
+                out = run(lib, frames, yuv=any_yuv, surface=True, kernel=kernel, ctas=2, seed=9, **kw)
+                check(oracle, frames, out, list(any_yuv), kw["hist_comp"], kw["wave_comp"], kw["vscope"],
+                      f"{variant} surface {kw} kernel {kernel}")
+
+
+@pytest.mark.parametrize("variant", ["default", "w8", "straight", "rawflat"])
+def test_saturation_and_flat_blocks(emul_libs, oracle, pkg, variant):
+    """a solid frame: one vectorscope bin takes every pixel (more than the 0x8000 a half-word bin may hold before
+    adds are taken back), waveform bins saturate at 255, the flat-block path is the one that runs; plus a frame
+    that is solid except for a few pixels, which defeats the flat path on some blocks"""
+    lib = emul_libs[variant]
+    w, h = 96, 400                       # 38 400 pixels > 32 768
+    solid = pkg.frames.solid(w, h, (200, 17, 90, 255))
+    speck = solid.copy()
+    speck[::37, ::11] = (3, 250, 128, 255)
+    speck[5::53, 7::13, 3] = 0           # and some transparent pixels
+    frames = np.stack([solid, speck])
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    out = run(lib, frames, ctas=1, seed=11)
+    check(oracle, frames, out, yuv, 0x07, 0x07, True, variant)
+    assert out[2][0].max() == 255 and out[1][0].max() == 255
+
+
+def test_scheduler_seeds_and_late_tma(emul_libs, oracle, pkg):
+    """the shipped kernel under many interleavings, including TMA loads that almost never land promptly"""
+    lib = emul_libs["default"]
+    frames = small_batch(pkg)[:2]
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    for seed in range(6):
+        out = run(lib, frames, ctas=1 + seed % 3, seed=100 + seed, land=(1, 10, 60)[seed % 3])
+        check(oracle, frames, out, yuv, 0x07, 0x07, True, f"seed {seed}")

@@ -183,7 +183,7 @@ def test_oracle_matches_reference_loops_random_geometry(oracle, ref):
 
 def test_transform_coefficients_are_the_effect_files(oracle):
     """The 18 coefficients of data/common.effect:23-43, read from the reference's file itself (build container
-    only), are the ones the product multiplies by (coef_for in csrc/scope_ffi.cu, as integers x 10^6) and the ones
+    only), are the ones the product multiplies by (coef_for in csrc/scope_kernels.cuh, as integers x 10^6) and the ones
     the oracle's table is made from (checked through the table: one channel at a time, two colours each)."""
     import re
     effect = "/root/reference/data/common.effect"
@@ -203,7 +203,7 @@ def test_transform_coefficients_are_the_effect_files(oracle):
         got[cs] = [[round(float(c) * 10 ** 6) for c in rows[ch][0]] for ch in "uyv"]
         assert all(len(c.split(".")[1]) == 6 for ch in "uyv" for c in rows[ch][0]), "six decimals: S is an integer"
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "obs-color-monitor_b200", "csrc",
-                            "scope_ffi.cu")).read()
+                            "scope_kernels.cuh")).read()
     for cs, tag in ((1, "k601"), (2, "k709")):
         m = re.search(tag + r"\[3\]\[3\]\s*=\s*\{(.*?)\};", src, re.S)
         product = [int(v) for v in re.findall(r"[+-]?\d+", m.group(1))]
