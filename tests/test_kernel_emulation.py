@@ -53,25 +53,42 @@ def masks(comp):
 
 
 def run(lib, frames, yuv=None, surface=False, hist_comp=0x07, wave_comp=0x07, vscope=True, kernel=K_TMA, ctas=2,
-        seed=1, colorspace=2, land=30):
-    """frames: (n, H, W, 4) u8.  hist_comp and wave_comp must select the same plane (one launch)."""
-    frames = np.ascontiguousarray(frames)
+        seed=1, colorspace=2, land=30, width=None, partial_into=None, x_offset=0, out_width=None, rows=None):
+    """frames: (n, H, W, 4) u8.  hist_comp and wave_comp must select the same plane (one launch).
+    width < W reads only the first `width` pixels of every (then pitched) row; rows = (y0, y1) reads a row band;
+    partial_into = (hist, wave_pairs, acc) accumulates a tile of a larger frame into shared partial results."""
+    assert frames.flags["C_CONTIGUOUS"]
     n, h, w, _ = frames.shape
+    pitch_w = w
+    if width is not None:
+        w = width
+    base = frames.ctypes.data
+    if rows is not None:
+        base += rows[0] * pitch_w * 4
+        h_band = rows[1] - rows[0]
+    else:
+        h_band = h
     hsrc, hmask = masks(hist_comp)
     wsrc, wmask = masks(wave_comp)
     src = hsrc if hsrc != SRC_NONE else wsrc
     assert wsrc in (SRC_NONE, src)
-    hist = np.zeros((n, 1024), np.uint32)
-    wave = np.full((n, 256, w, 4), 0xEE, np.uint8)      # the kernel must write every row it owns
-    acc = np.zeros((n, 65536), np.uint32)
+    ow = out_width or w
+    wave = np.full((n, 256, ow, 4), 0xEE, np.uint8)     # the kernel must write every row it owns
+    if partial_into is None:
+        hist = np.zeros((n, 1024), np.uint32)
+        acc = np.zeros((n, 65536), np.uint32)
+        pairs = None
+    else:
+        hist, pairs, acc = partial_into
     rq = Request()
-    rq.rgb = frames.ctypes.data
-    rq.yuv = yuv.ctypes.data if yuv is not None else None
-    rq.linesize, rq.width, rq.height, rq.n_frames, rq.frame_stride = w * 4, w, h, n, w * h * 4
+    rq.rgb = base
+    rq.yuv = yuv.ctypes.data + (base - frames.ctypes.data) if yuv is not None else None
+    rq.linesize, rq.width, rq.height, rq.n_frames, rq.frame_stride = pitch_w * 4, w, h_band, n, pitch_w * h * 4
     rq.colorspace, rq.surface, rq.src, rq.vscope = colorspace, int(surface), src, int(vscope)
     rq.bins_mask, rq.hist_mask, rq.wave_mask = hmask | wmask, hmask, wmask
     rq.hist, rq.wave, rq.vs_acc = hist.ctypes.data, wave.ctypes.data, acc.ctypes.data
-    rq.out_width, rq.x_offset, rq.partial = w, 0, 0
+    rq.wave_pairs = pairs.ctypes.data if pairs is not None else None
+    rq.out_width, rq.x_offset, rq.partial = ow, x_offset, int(partial_into is not None)
     rq.kernel, rq.ctas, rq.seed, rq.tma_land_percent = kernel, ctas, seed, land
     rc = lib.emul_run(C.byref(rq))
     assert rc == 0, rq.error.decode()
@@ -164,3 +181,37 @@ def test_scheduler_seeds_and_late_tma(emul_libs, oracle, pkg):
     for seed in range(6):
         out = run(lib, frames, ctas=1 + seed % 3, seed=100 + seed, land=(1, 10, 60)[seed % 3])
         check(oracle, frames, out, yuv, 0x07, 0x07, True, f"seed {seed}")
+
+
+@pytest.mark.parametrize("variant", ["default", "w8_straight"])
+def test_pitched_rows_and_tile_sharded_frames(emul_libs, oracle, pkg, variant):
+    """rows with padding behind them, the plain-load kernel on a plane that is only pixel-aligned, and one frame
+    accumulated as two row bands + two column bands into shared partial results (the multi-GPU tile sharding:
+    u32 histogram, u16-pair waveform planes, u32 vectorscope; saturation after the sum)"""
+    lib = emul_libs[variant]
+    rng = np.random.default_rng(8)
+    wide = rng.integers(0, 256, (1, 140, 104, 4), dtype=np.uint8)       # 104-pixel pitch, garbage in the padding
+    wide[..., 3] = np.where(rng.random((1, 140, 104)) < 0.1, 0, 255)
+    w = 77
+    f = np.ascontiguousarray(wide[:, :, :w])
+    yuv = [oracle.rgb_to_yuv(f[0], 2)]
+    out = run(lib, wide, width=w, ctas=2, seed=3)                        # pitch 416 bytes = 26 x 16: TMA
+    check(oracle, f, out, yuv, 0x07, 0x07, True, f"{variant} pitched")
+    # a crop that starts at an odd column is only 4-byte aligned: the plain-load kernel's job
+    crop = wide.reshape(-1)[3 * 4:][: 139 * 104 * 4].reshape(1, 139, 104, 4)
+    fc = np.ascontiguousarray(crop[:, :, :w])
+    out = run(lib, crop, width=w, kernel=K_LDG, ctas=2, seed=4)
+    check(oracle, fc, out, [oracle.rgb_to_yuv(fc[0], 2)], 0x07, 0x07, True, f"{variant} unaligned crop")
+    # tile sharding: rows [0, 64) and [64, 140) of the full width, accumulated into the same partial buffers
+    full = np.ascontiguousarray(wide[:, :, :96])
+    hist = np.zeros((1, 1024), np.uint32)
+    pairs = np.zeros((2, 256, 96), np.uint32)
+    acc = np.zeros((1, 65536), np.uint32)
+    for band in ((0, 64), (64, 140)):
+        run(lib, wide, width=96, rows=band, partial_into=(hist, pairs, acc), ctas=2, seed=band[0] + 5)
+    y = oracle.rgb_to_yuv(full[0], 2)
+    assert np.array_equal(hist[0], oracle.histogram_counts(0x07, full[0], y))
+    wave = np.stack([np.minimum(pairs[0] & 0xFFFF, 255), np.minimum(pairs[0] >> 16, 255), np.minimum(pairs[1] & 0xFFFF, 255)],
+                    axis=-1).astype(np.uint8)
+    assert np.array_equal(wave, oracle.waveform(0x07, full[0], y)[..., :3])
+    assert np.array_equal(np.minimum(acc[0], 255).astype(np.uint8).reshape(256, 256), oracle.vectorscope(y))
