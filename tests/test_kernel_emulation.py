@@ -215,3 +215,18 @@ def test_pitched_rows_and_tile_sharded_frames(emul_libs, oracle, pkg, variant):
                     axis=-1).astype(np.uint8)
     assert np.array_equal(wave, oracle.waveform(0x07, full[0], y)[..., :3])
     assert np.array_equal(np.minimum(acc[0], 255).astype(np.uint8).reshape(256, 256), oracle.vectorscope(y))
+
+
+@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight"])
+def test_extreme_geometries(emul_libs, oracle, pkg, variant):
+    """one pixel, one row, one column, a narrow tall strip, exactly one tile, one row more than a tile"""
+    lib = emul_libs[variant]
+    for w, h in ((1, 1), (33, 1), (1, 97), (5, 300), (32, 64), (64, 65), (31, 63)):
+        f = pkg.frames.random(w, h, seed=w * 1000 + h)[None]
+        f = np.ascontiguousarray(f)
+        yuv = [oracle.rgb_to_yuv(f[0], 2)]
+        for kernel in (K_TMA, K_LDG):
+            if kernel == K_TMA and (w * 4) % 16:
+                continue                 # the host sends pitches that are not a multiple of 16 to the plain-load kernel
+            out = run(lib, f, kernel=kernel, ctas=2, seed=w + h)
+            check(oracle, f, out, yuv, 0x07, 0x07, True, f"{variant} {w}x{h} kernel {kernel}")
