@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--frames-per-gpu", type=int, default=64)
     ap.add_argument("--width", type=int, default=WIDTH_4K)
     ap.add_argument("--height", type=int, default=HEIGHT_4K)
-    ap.add_argument("--content", default="mixed", choices=["mixed", "random", "natural", "ramp", "solid"])
+    ap.add_argument("--content", default="mixed", choices=["mixed", "random", "natural", "ramp", "solid", "ui"])
     ap.add_argument("--colorspace", type=int, default=2)
     ap.add_argument("--e2e-frames", type=int, default=16, help="frames per step on the host-buffer path")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="0 = one frame per host thread (bounded)")
@@ -129,10 +129,13 @@ class CpuReference:
         self.kind = "reference" if Ref.available() else "port"
         self.impl = Ref() if self.kind == "reference" else None
         self.threads, self.n = threads, n_frames
-        offset = {"mixed": None, "random": 0, "ramp": 1, "solid": 2, "natural": 3}[content]
+        offset = {"mixed": None, "random": 0, "ramp": 1, "solid": 2, "natural": 3, "ui": None}[content]
         self.frames = []
         for i in range(n_frames):
-            f = pkg.frames.mixed(width, height, i if offset is None else 4 * i + offset)
+            if content == "ui":
+                f = pkg.frames.ui(width, height, i)
+            else:
+                f = pkg.frames.mixed(width, height, i if offset is None else 4 * i + offset)
             self.frames.append((f, self.orc.rgb_to_yuv(f, colorspace)))
 
     def _work(self, i):
@@ -203,7 +206,8 @@ def metric_name(args):
 
 def workload_name(args):
     return (f"batch of {args.frames_per_gpu} independent {args.width}x{args.height} BGRA frames per GPU "
-            f"({args.content}: random/ramp/solid/natural cycle), fused histogram RGB + waveform RGB + "
+            f"({'mixed: random/ramp/solid/natural cycle' if args.content == 'mixed' else args.content + ' content'}), "
+            f"fused histogram RGB + waveform RGB + "
             f"vectorscope BT.{'601' if args.colorspace == 1 else '709'}, frame-sharded (BASELINE config 5; "
             f"metric quoted @3840x2160)")
 

@@ -85,6 +85,14 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_STRAIGHT
 #define SCOPE_STRAIGHT 0
 #endif
+//   SCOPE_BALLOT (experiment for round 2, OFF) almost-flat blocks - screen content: a flat background with a little
+//                 text in it - put nearly every lane of a warp on ONE vectorscope bin, and k lanes on one word
+//                 cost k cycles.  The flat test's vote becomes a ballot; when at least kBallotLanes lanes hold
+//                 nothing but the reference bin (lane 0's first pixel), every pixel of the block that hits that
+//                 bin is counted with per-row ballots and added by one lane, the rest go their usual way.
+#ifndef SCOPE_BALLOT
+#define SCOPE_BALLOT 0
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -108,6 +116,7 @@ constexpr int kGroupWarps = SCOPE_GROUP_WARPS > 0 ? SCOPE_GROUP_WARPS : 24; // c
 constexpr int kGroupRows = 4;                    // rows per group == rows one ldmatrix.x4 reads
 constexpr int kSplitVsWarps = SCOPE_SPLIT_VS_WARPS;   // specialised kernel: warps doing transform + vectorscope
 constexpr int kSplitBinWarps = SCOPE_SPLIT_BIN_WARPS; // specialised kernel: warps doing the column bins
+constexpr int kBallotLanes = 8;            // SCOPE_BALLOT: lanes that must agree before a block takes the aggregating path
 constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
 constexpr int kMaxStages = 8;              // upper bound of the ring depth (barrier storage)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
@@ -885,6 +894,10 @@ struct Prep {
 #if SCOPE_RAWFLAT
 	bool rawflat;      // warp-uniform: all N x 32 pixel words are equal; only element [0] is filled in
 #endif
+#if SCOPE_BALLOT
+	bool dominant;     // warp-uniform: not flat, but many lanes hold only the reference bin `ref`
+	uint32_t ref;      // warp-uniform: lane 0's first vectorscope bin
+#endif
 };
 
 template <int SRC, bool VSCOPE, bool SURFACE, int N>
@@ -971,8 +984,21 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 		for (int k = 1; k < N; k++)
 			same = same && (o.idx[k] == o.idx[0]);
 		const uint32_t idx_lane0 = __shfl_sync(0xFFFFFFFFu, o.idx[0], 0);
+#if SCOPE_BALLOT
+		const uint32_t agree = __ballot_sync(0xFFFFFFFFu, same && (o.idx[0] == idx_lane0));
+		o.flat = agree == 0xFFFFFFFFu;
+		o.dominant = !o.flat && __popc(agree) >= kBallotLanes;
+		o.ref = idx_lane0;
+#else
 		o.flat = __all_sync(0xFFFFFFFFu, same && (o.idx[0] == idx_lane0));
+#endif
 	}
+#if SCOPE_BALLOT
+	else {
+		o.dominant = false;
+		o.ref = 0;
+	}
+#endif
 }
 
 // commit_issue: every shared-memory atomic of the tile.  The vectorscope adds return the old
@@ -1030,6 +1056,24 @@ __device__ __forceinline__ void commit_issue(const TileCtx &c, const Prep<N> &o,
 			if (c.lane == 0)
 				vs_undo(vs_add(c.vs_base, o.idx[0], 32u * N));
 			// sass-cold}
+#if SCOPE_BALLOT
+		} else if (o.dominant) {
+			// sass-cold{
+			// every pixel of the block that hits the reference bin is counted by ballot and added once;
+			// the others are added one by one, checked right away (nothing is left for commit_resolve)
+			uint32_t n_ref = 0;
+#pragma unroll
+			for (int k = 0; k < N; k++) {
+				const bool hit = o.idx[k] == o.ref;
+				n_ref += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, hit));
+				if (!hit)
+					vs_undo(vs_add(c.vs_base, o.idx[k], 1u));
+				pend[k] = 0u;
+			}
+			if (c.lane == 0)
+				vs_undo(vs_add(c.vs_base, o.ref, n_ref));
+			// sass-cold}
+#endif
 		} else {
 #pragma unroll
 			for (int k = 0; k < N; k++) {
@@ -1279,6 +1323,9 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					bool ordinary = !cur.flat && (R_SRC == SRC_NONE || (cur.all_counted && tc.bins_mask == 7u));
 #if SCOPE_RAWFLAT
 					ordinary = ordinary && !cur.rawflat;
+#endif
+#if SCOPE_BALLOT
+					ordinary = ordinary && !cur.dominant;
 #endif
 					if (ordinary) {
 						release_tile(bar2, p, q);

@@ -8,6 +8,7 @@ The definitions are the ones SURVEY.md §8(d) fixes for BASELINE.json's configs:
 * ``alpha_stripes``  random colours, every ``period``-th column fully transparent
   (exercises the ``a == 0`` skip of histogram.c:385-387 / waveform.c:246-248)
 * ``natural`` smooth gradients + low-amplitude noise (video-like bin locality)
+* ``ui``      screen-capture-like: flat background with text lines (almost-flat blocks; not part of ``mixed``)
 """
 from __future__ import annotations
 
@@ -62,6 +63,25 @@ def natural(width: int, height: int, seed: int = 0) -> np.ndarray:
         n = rng.integers(-3, 4, size=(height, width), dtype=np.int16)
         f[..., c] = np.clip(base[c] + n, 0, 255).astype(np.uint8)
     f[..., 3] = 255
+    return f
+
+
+def ui(width: int, height: int, seed: int = 0) -> np.ndarray:
+    """Screen-capture-like content (an editor window): a flat dark background, 12-pixel text lines every 24 rows
+    with ~25 % ink in two colours.  Most 4 x 32 blocks are *almost* flat: nearly every lane of a warp hits the
+    background's vectorscope bin, the worst case for same-bin serialisation that the mixed batch does not contain."""
+    x = np.arange(width, dtype=np.int64)[None, :]
+    y = np.arange(height, dtype=np.int64)[:, None]
+    f = np.empty((height, width, 4), np.uint8)
+    f[...] = (34, 30, 30, 255)
+    line = (y % 24 >= 6) & (y % 24 < 18)
+    h = (((x // 2) * 73856093) ^ ((y // 2) * 19349663) ^ (seed * 83492791)) & 0xFFFFFFFF
+    glyph = line & (((h >> 7) & 3) == 0) & (x % 512 < 400)
+    word = ((((x // 64) * 2654435761) ^ ((y // 24) * 40503) ^ seed) & 0xFFFFFFFF) >> 11
+    accent = (word % 5 == 0) & glyph
+    plain = glyph & ~accent
+    f[plain] = (220, 220, 220, 255)
+    f[accent] = (90, 200, 255, 255)
     return f
 
 

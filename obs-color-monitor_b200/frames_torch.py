@@ -48,6 +48,23 @@ def _natural(w, h, dev, seed):
     return f
 
 
+def _ui(w, h, dev, seed):
+    """frames.ui on the device (integer arithmetic only: bit-identical to the numpy version)"""
+    x = torch.arange(w, device=dev, dtype=torch.int64)[None, :]
+    y = torch.arange(h, device=dev, dtype=torch.int64)[:, None]
+    f = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
+    f[..., 0], f[..., 1], f[..., 2], f[..., 3] = 34, 30, 30, 255
+    line = (y % 24 >= 6) & (y % 24 < 18)
+    hsh = (((x // 2) * 73856093) ^ ((y // 2) * 19349663) ^ (seed * 83492791)) & 0xFFFFFFFF
+    glyph = line & (((hsh >> 7) & 3) == 0) & (x % 512 < 400)
+    word = ((((x // 64) * 2654435761) ^ ((y // 24) * 40503) ^ seed) & 0xFFFFFFFF) >> 11
+    accent = (word % 5 == 0) & glyph
+    plain = glyph & ~accent
+    f[plain] = torch.tensor([220, 220, 220, 255], dtype=torch.uint8, device=dev)
+    f[accent] = torch.tensor([90, 200, 255, 255], dtype=torch.uint8, device=dev)
+    return f
+
+
 def mixed_frame(w: int, h: int, index: int, dev) -> torch.Tensor:
     k = index % 4
     if k == 0:
@@ -74,6 +91,8 @@ def mixed_batch(n: int, w: int, h: int, dev, first_index: int = 0, content: str 
             out[i] = _ramp(w, h, dev)
         elif content == "solid":
             out[i] = _solid(w, h, dev, idx)
+        elif content == "ui":
+            out[i] = _ui(w, h, dev, idx)
         else:
             raise ValueError(content)
     return out

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "simt", "_build")
 SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
           [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", "scope_kernels.cuh")]
-VARIANTS = ["default", "w8", "w12n6", "w12n8", "w16n6_straight", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+VARIANTS = ["default", "w8", "w12n6", "w12n8", "w16n6_straight", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
 SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
 K_TMA, K_LDG, K_GROUP = 0, 1, 2
 
@@ -171,6 +171,22 @@ def test_saturation_and_flat_blocks(emul_libs, oracle, pkg, variant):
     out = run(lib, frames, ctas=1, seed=11)
     check(oracle, frames, out, yuv, 0x07, 0x07, True, variant)
     assert out[2][0].max() == 255 and out[1][0].max() == 255
+
+
+@pytest.mark.parametrize("variant", ["default", "ballot", "w8_straight_ballot"])
+def test_almost_flat_blocks(emul_libs, oracle, pkg, variant):
+    """screen-like content: a flat background with text in it.  Most blocks are not flat but most lanes sit on
+    the background's bin - the case SCOPE_BALLOT aggregates (and the shipped kernel must get right the slow way);
+    96 x 400 keeps the background bin above 0x8000 so that the take-back of aggregated adds is exercised too"""
+    lib = emul_libs[variant]
+    frames = np.stack([pkg.frames.ui(96, 400, 1), pkg.frames.ui(96, 400, 2)])
+    frames[1, 100:140, 10:50] = pkg.frames.random(40, 40, 3)        # a picture inside the window
+    frames[1, ::29, ::7, 3] = 0                                      # and some transparent pixels
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    out = run(lib, frames, ctas=2, seed=21)
+    check(oracle, frames, out, yuv, 0x07, 0x07, True, variant)
+    out = run(lib, frames, hist_comp=0, wave_comp=0, ctas=1, seed=22)      # vectorscope only
+    check(oracle, frames, out, yuv, 0, 0, True, variant + " vectorscope only")
 
 
 def test_scheduler_seeds_and_late_tma(emul_libs, oracle, pkg):

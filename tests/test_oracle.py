@@ -216,3 +216,16 @@ def test_transform_coefficients_are_the_effect_files(oracle):
             for ch in range(3):
                 s = sum(c * v for c, v in zip(got[cs][ch], rgb)) + off[ch]
                 assert (word >> (8 * ch)) & 0xFF == s // 10 ** 6
+
+
+def test_device_side_generators_match_frames_py(pkg):
+    """the integer-only frame families are bit-identical on the torch side (bench.py's bulk data) and in
+    frames.py (what the parity tests and the CPU baseline use)"""
+    import torch
+    from obs_color_monitor_b200 import frames_torch
+    cpu = torch.device("cpu")
+    for seed in (0, 7):
+        assert np.array_equal(pkg.frames.ui(700, 130, seed),
+                              frames_torch.mixed_batch(1, 700, 130, cpu, first_index=seed, content="ui")[0].numpy())
+    assert np.array_equal(pkg.frames.ramp(300, 77), frames_torch.mixed_batch(1, 300, 77, cpu, content="ramp")[0].numpy())
+    assert np.array_equal(pkg.frames.mixed(64, 48, 6), frames_torch.mixed_batch(1, 64, 48, cpu, first_index=6, content="solid")[0].numpy())

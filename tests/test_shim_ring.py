@@ -524,17 +524,20 @@ def test_capture_core_matches_the_reference(shim, pkg, flags, roi):
         R.refc_set_roi(ref, *roi)
         lib.b200_cm_set_roi(C.byref(cm), roi[0], roi[1], roi[2], roi[3], W, H)
 
+    # settled = the worker has nothing left it could do: it waits for work, or - only while the gate is closed -
+    # it sits inside the callback (with the gate open, "inside" is a state that is about to change)
     def ref_settled():
-        return inside["ref"] or R.refc_idle(ref)
+        return (inside["ref"] and not gate.is_set()) or (R.refc_idle(ref) and not inside["ref"])
 
     def shim_settled():
         nxt = (cm.i_read_queue + 1) % 3
-        return inside["shim"] or ((cm.i_write_queue == nxt or cm.i_staging_queue == nxt) and not cm.worker_busy)
+        idle = (cm.i_write_queue == nxt or cm.i_staging_queue == nxt) and not cm.worker_busy and not inside["shim"]
+        return (inside["shim"] and not gate.is_set()) or idle
 
     def settle():
         for who in (ref_settled, shim_settled):
             ok = 0
-            for _ in range(4000):            # the worker is either waiting for work or inside the callback
+            for _ in range(40000):           # the worker is either waiting for work or inside the callback
                 ok = ok + 1 if who() else 0
                 if ok >= 3:
                     break

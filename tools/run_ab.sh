@@ -22,6 +22,7 @@ for v in $(ls variants_tmp/*.so 2>/dev/null); do
   if [ $rc -eq 0 ]; then
     SCOPE_LIB=$PWD/$v $B > $O/${n}_mixed.json 2>/dev/null
     SCOPE_LIB=$PWD/$v $B --content natural > $O/${n}_natural.json 2>/dev/null
+    case $n in *ballot*) SCOPE_LIB=$PWD/$v $B --content ui > $O/${n}_ui.json 2>/dev/null;; esac
   fi
 done
 for n in deepring w8_deepring; do   # what the deeper rings are for: the passes with room to spare
@@ -32,7 +33,7 @@ for n in deepring w8_deepring; do   # what the deeper rings are for: the passes 
 done
 SCOPE_KERNEL=group $B > $O/group_mixed.json 2>/dev/null
 if [ "$1" != "quick" ]; then
-  for c in random natural solid ramp; do $B --content $c > $O/new_$c.json 2>/dev/null; done
+  for c in random natural solid ramp ui; do $B --content $c > $O/new_$c.json 2>/dev/null; done
   $B --scopes wave > $O/new_waveonly.json 2>/dev/null
   $B --scopes hist > $O/new_histonly.json 2>/dev/null
   $B --scopes hist,wave > $O/new_histwave.json 2>/dev/null

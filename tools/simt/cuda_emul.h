@@ -157,7 +157,7 @@ template <class F> inline void rendezvous(Rendezvous &rv, int n, F on_complete)
 inline Warp &my_warp() { return W->cur->cta->warps[W->cur->tid >> 5]; }
 inline int my_lane() { return (int)(W->cur->tid & 31); }
 
-enum Op { OP_SHFL, OP_ALL, OP_ANY, OP_ADD, OP_SYNC };
+enum Op { OP_SHFL, OP_ALL, OP_ANY, OP_ADD, OP_SYNC, OP_BALLOT };
 
 // full-mask warp collective on one 32-bit value per lane (src_lane only for OP_SHFL)
 inline uint32_t collective(Op op, uint32_t v, int src_lane = 0)
@@ -179,6 +179,9 @@ inline uint32_t collective(Op op, uint32_t v, int src_lane = 0)
 				r += w.vals[b][i];
 		} else if (op == OP_SHFL) {
 			r = w.vals[b][src_lane & 31];
+		} else if (op == OP_BALLOT) {
+			for (int i = 0; i < 32; i++)
+				r |= (w.vals[b][i] ? 1u : 0u) << i;
 		}
 		for (int i = 0; i < 32; i++)
 			w.res[b][i][0] = r;
@@ -329,6 +332,8 @@ static inline uint32_t __shfl_sync(uint32_t, uint32_t v, int lane) { return emul
 static inline bool __all_sync(uint32_t, bool p) { return emul::collective(emul::OP_ALL, p) != 0; }
 static inline bool __any_sync(uint32_t, bool p) { return emul::collective(emul::OP_ANY, p) != 0; }
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return emul::collective(emul::OP_ADD, v); }
+static inline uint32_t __ballot_sync(uint32_t, bool p) { return emul::collective(emul::OP_BALLOT, p); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline void __syncwarp() { emul::collective(emul::OP_SYNC, 0); }
 static inline void __syncthreads() { emul::bar_sync(0, (int)emul::W->cur->cta->block_dim); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v)
