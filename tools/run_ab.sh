@@ -41,6 +41,8 @@ if [ "$1" != "quick" ]; then
   $B --width 1920 --height 1080 > $O/new_1080p.json 2>/dev/null
   $B --width 7680 --height 4320 --frames-per-gpu 16 > $O/new_8k.json 2>/dev/null
 fi
+# the open micro-benchmark questions of DESIGN 8.1 (build tools/ubench2 first; about a minute)
+[ -x tools/ubench2 ] && bash tools/run_ubench2.sh > /dev/null 2>&1
 echo "== pytest (in-tree)"; cat $O/pytest.log
 for f in $O/pytest_*.full; do echo "$f: $(tail -2 $f | tr '\n' ' ')"; done
 for f in $O/*.json; do echo $f $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(round(d['value']), round(d['roofline']['frac'],4), d['clocks']['sm_mhz'])" 2>&1 | tail -1); done
