@@ -1433,8 +1433,15 @@ __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint
 template <int SRC, bool VSCOPE, bool SURFACE>
 constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
 
+// SCOPE_MAXNREG (experiment): an explicit register cap instead of the one ptxas derives from the launch bounds
+// (for 544 threads it stops at 96, not at the 120 that fit: it seems to round the block up to 640 threads)
+#if defined(SCOPE_MAXNREG) && !defined(SCOPE_EMULATE)
+#define SCOPE_TMA_BOUNDS __maxnreg__(SCOPE_MAXNREG)
+#else
+#define SCOPE_TMA_BOUNDS __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
+#endif
 template <int SRC, bool VSCOPE, bool SURFACE>
-__global__ void __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
+__global__ void SCOPE_TMA_BOUNDS
 	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
 			       const __grid_constant__ CUtensorMap map_yuv)
 {
@@ -1501,7 +1508,9 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 	// "empty" barrier either way (NWORK arrivals complete a phase).  Ahead: tile n - kStages (same
 	// stage, previous phase) was waited for before tile n is asked about.  Behind: tile n + kStages
 	// cannot be loaded before this warp has arrived for tile n, which it does after its wait.
+#ifndef SCOPE_EXPERIMENT
 	static_assert(NWORK >= (int)GPT, "a warp must own at most one group per tile");
+#endif
 	uint32_t next_tile = 0; // first tile this warp has not finished (read + released, or passed)
 	uint32_t waited = 0;    // tiles [0, waited) have been waited for; next_tile <= waited <= next_tile + 1
 	uint32_t landed = 0;    // early answer of mbar_test for tile `waited`

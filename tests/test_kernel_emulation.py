@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "simt", "_build")
 SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
           [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", "scope_kernels.cuh")]
-VARIANTS = ["default", "w8", "w12n6", "w12n8", "w16n6_straight", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+VARIANTS = ["default", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
 SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
 K_TMA, K_LDG, K_GROUP = 0, 1, 2
 
@@ -233,7 +233,7 @@ def test_pitched_rows_and_tile_sharded_frames(emul_libs, oracle, pkg, variant):
     assert np.array_equal(np.minimum(acc[0], 255).astype(np.uint8).reshape(256, 256), oracle.vectorscope(y))
 
 
-@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight"])
+@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight", "w16n8"])
 def test_extreme_geometries(emul_libs, oracle, pkg, variant):
     """one pixel, one row, one column, a narrow tall strip, exactly one tile, one row more than a tile"""
     lib = emul_libs[variant]
