@@ -133,7 +133,7 @@ bool use_group_kernel()
 }
 
 template <int SRC, bool VS, bool SURF>
-void kernel_entry(bool tma, KernelChoice &k)
+void kernel_entry(bool tma, int colorspace, KernelChoice &k)
 {
 	if (tma && use_group_kernel()) {
 		k.tma = scope_strip_kernel_tmag<SRC, VS, SURF>;
@@ -141,6 +141,11 @@ void kernel_entry(bool tma, KernelChoice &k)
 		k.threads = kGroupWarps * 32 + 32;
 	} else if (tma) {
 		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
+#if SCOPE_IMMCOEF
+		// the kernels that evaluate the transform exist once per colour space, coefficients as immediates
+		if (!SURF && (VS || SRC == SRC_YUV))
+			k.tma = colorspace == 1 ? scope_strip_kernel_tma<SRC, VS, SURF, 1> : scope_strip_kernel_tma<SRC, VS, SURF, 2>;
+#endif
 		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
 		k.threads = kTmaWarps * 32 + 32;
 	} else {
@@ -151,24 +156,24 @@ void kernel_entry(bool tma, KernelChoice &k)
 }
 
 template <bool SURF>
-bool pick_kernel2(int src, bool vs, bool tma, KernelChoice &k)
+bool pick_kernel2(int src, bool vs, bool tma, int colorspace, KernelChoice &k)
 {
 	if (src == SRC_NONE && vs)
-		kernel_entry<SRC_NONE, true, SURF>(tma, k);
+		kernel_entry<SRC_NONE, true, SURF>(tma, colorspace, k);
 	else if (src == SRC_RGB && vs)
-		kernel_entry<SRC_RGB, true, SURF>(tma, k);
+		kernel_entry<SRC_RGB, true, SURF>(tma, colorspace, k);
 	else if (src == SRC_RGB && !vs)
-		kernel_entry<SRC_RGB, false, SURF>(tma, k);
+		kernel_entry<SRC_RGB, false, SURF>(tma, colorspace, k);
 	else if (src == SRC_YUV && vs)
-		kernel_entry<SRC_YUV, true, SURF>(tma, k);
+		kernel_entry<SRC_YUV, true, SURF>(tma, colorspace, k);
 	else if (src == SRC_YUV && !vs)
-		kernel_entry<SRC_YUV, false, SURF>(tma, k);
+		kernel_entry<SRC_YUV, false, SURF>(tma, colorspace, k);
 	else
 		return false;
 	return true;
 }
 
-bool pick_kernel(int src, bool vs, bool surface, bool tma, KernelChoice &k)
+bool pick_kernel(int src, bool vs, bool surface, bool tma, int colorspace, KernelChoice &k)
 {
 	// experiment kept for A/B runs (profiles/ubench_r01.md): SCOPE_SPLIT=1 selects the
 	// warp-specialised kernel for the headline combination; it measured no faster
@@ -184,7 +189,7 @@ bool pick_kernel(int src, bool vs, bool surface, bool tma, KernelChoice &k)
 		k.threads = (kSplitVsWarps + kSplitBinWarps) * 32 + 32;
 		return true;
 	}
-	return surface ? pick_kernel2<true>(src, vs, tma, k) : pick_kernel2<false>(src, vs, tma, k);
+	return surface ? pick_kernel2<true>(src, vs, tma, colorspace, k) : pick_kernel2<false>(src, vs, tma, colorspace, k);
 }
 
 int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x_extent_px, uint32_t linesize,
@@ -311,7 +316,7 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	}
 
 	KernelChoice k;
-	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, k))
+	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
 		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
 	const void *fn = use_tma ? (const void *)k.tma : (const void *)k.ldg;
 	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));

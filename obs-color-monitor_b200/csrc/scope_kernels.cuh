@@ -93,6 +93,12 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_BALLOT
 #define SCOPE_BALLOT 0
 #endif
+//   SCOPE_IMMCOEF (experiment for round 2, OFF) the TMA tile kernel is instantiated per colour space and takes the
+//                 transform's coefficients as compile-time constants (IMAD with an immediate operand) instead of
+//                 twelve registers loaded from the launch parameters - registers a wider tile visit can use
+#ifndef SCOPE_IMMCOEF
+#define SCOPE_IMMCOEF 0
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -349,6 +355,26 @@ inline Coef coef_for(int colorspace)
 		}
 		*adds[ch] = k_add[ch] - sum * kCarrierBias;
 	}
+	return c;
+}
+
+// the same numbers as compile-time constants (SCOPE_IMMCOEF); CS = 1: BT.601, 2: BT.709
+template <int CS>
+__device__ __forceinline__ constexpr Coef const_coef()
+{
+	constexpr int32_t m[3][3] = {{CS == 1 ? -147643 : -100643, CS == 1 ? -289855 : -338571, CS == 1 ? 437500 : 439216},
+				     {CS == 1 ? 299000 : 212600, CS == 1 ? 587000 : 715200, CS == 1 ? 114000 : 72200},
+				     {CS == 1 ? 437500 : 439216, CS == 1 ? -366351 : -398941, CS == 1 ? -71147 : -40273}};
+	constexpr uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
+	Coef c{};
+	for (int i = 0; i < 3; i++) {
+		c.u[i] = (uint32_t)m[0][i];
+		c.y[i] = (uint32_t)m[1][i];
+		c.v[i] = (uint32_t)m[2][i];
+	}
+	c.ku = k_add[0] - ((uint32_t)m[0][0] + (uint32_t)m[0][1] + (uint32_t)m[0][2]) * kCarrierBias;
+	c.ky = k_add[1] - ((uint32_t)m[1][0] + (uint32_t)m[1][1] + (uint32_t)m[1][2]) * kCarrierBias;
+	c.kv = k_add[2] - ((uint32_t)m[2][0] + (uint32_t)m[2][1] + (uint32_t)m[2][2]) * kCarrierBias;
 	return c;
 }
 
@@ -1189,7 +1215,7 @@ __device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensor
 // One consumer warp's walk over the chunks.  R_SRC / R_VS = what THIS warp accumulates (its
 // role), N = rows of every tile it takes starting at `row0`; K_BINS / K_VS = what the kernel as
 // a whole holds in shared memory (all NWORK consumer warps meet in emit_strip / flush_vscope).
-template <class L, int R_SRC, bool R_VS, bool SURFACE, int N, int NWORK, bool K_BINS, bool K_VS>
+template <class L, int R_SRC, bool R_VS, bool SURFACE, int N, int NWORK, bool K_BINS, bool K_VS, int CS = 0>
 __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem, uint32_t smem_base,
 					    volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty,
 					    int row0, int warp, int lane, int tid)
@@ -1205,7 +1231,12 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	magic = opaque_carrier_bias();
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
 			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
-	const Coef coef = P.coef;
+	// CS != 0 (SCOPE_IMMCOEF): the nine multipliers are compile-time constants; the three addends stay in
+	// registers (an IMAD takes one immediate, and with both constant ptxas spends an extra move per pixel)
+	Coef coef = CS ? const_coef<CS ? CS : 2>() : P.coef;
+	coef.ku = P.coef.ku;
+	coef.ky = P.coef.ky;
+	coef.kv = P.coef.kv;
 	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
 	zero = opaque_zero();
 	uint32_t stage = 0, phase = 0, qr = 0;
@@ -1440,7 +1471,7 @@ constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
 #else
 #define SCOPE_TMA_BOUNDS __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
 #endif
-template <int SRC, bool VSCOPE, bool SURFACE>
+template <int SRC, bool VSCOPE, bool SURFACE, int CS = 0>
 __global__ void SCOPE_TMA_BOUNDS
 	scope_strip_kernel_tma(const __grid_constant__ StripParams P, const __grid_constant__ CUtensorMap map_rgb,
 			       const __grid_constant__ CUtensorMap map_yuv)
@@ -1461,8 +1492,8 @@ __global__ void SCOPE_TMA_BOUNDS
 			tma_produce<L>(P, &map_rgb, &map_yuv, smem_base, chunk_q, bar_full, bar_empty);
 		return;
 	}
-	tma_consume<L, SRC, VSCOPE, SURFACE, RPW, NW, SRC != SRC_NONE, VSCOPE>(P, smem, smem_base, chunk_q, bar_full,
-									      bar_empty, warp * RPW, warp, lane, tid);
+	tma_consume<L, SRC, VSCOPE, SURFACE, RPW, NW, SRC != SRC_NONE, VSCOPE, CS>(P, smem, smem_base, chunk_q, bar_full,
+										  bar_empty, warp * RPW, warp, lane, tid);
 }
 
 // ---------------------------------------------------------------------------

@@ -42,13 +42,23 @@ struct Launch {
 	StripParams P;
 	CUtensorMap map_rgb, map_yuv;
 	int kernel;
-	int src, vs, surf;
+	int src, vs, surf, colorspace;
 };
 
 template <int SRC, bool VS, bool SURF> void call_kernel(const Launch &l)
 {
-	if (l.kernel == 0)
+	if (l.kernel == 0) {
+#if SCOPE_IMMCOEF
+		if (!SURF && (VS || SRC == SRC_YUV)) { // what kernel_entry (csrc/scope_ffi.cu) picks in these builds
+			if (l.colorspace == 1)
+				scope_strip_kernel_tma<SRC, VS, SURF, 1>(l.P, l.map_rgb, l.map_yuv);
+			else
+				scope_strip_kernel_tma<SRC, VS, SURF, 2>(l.P, l.map_rgb, l.map_yuv);
+			return;
+		}
+#endif
 		scope_strip_kernel_tma<SRC, VS, SURF>(l.P, l.map_rgb, l.map_yuv);
+	}
 	else if (l.kernel == 2)
 		scope_strip_kernel_tmag<SRC, VS, SURF>(l.P, l.map_rgb, l.map_yuv);
 	else
@@ -150,6 +160,7 @@ extern "C" int emul_run(EmulRequest *rq)
 	l.src = rq->src;
 	l.vs = rq->vscope != 0;
 	l.surf = rq->surface != 0;
+	l.colorspace = rq->colorspace;
 
 	const bool need_rgb = !l.surf || l.src == SRC_RGB;
 	const bool need_yuv = l.surf && (l.src == SRC_YUV || l.vs);
@@ -274,7 +285,7 @@ extern "C" const char *emul_build_flags()
 {
 	static std::string s = std::string("warps=") + std::to_string(kTmaWarps) + " tile_rows=" + std::to_string(kTileRows) +
 			       " straight=" + std::to_string(SCOPE_STRAIGHT) + " rawflat=" + std::to_string(SCOPE_RAWFLAT) +
-			       " deep_ring=" + std::to_string(SCOPE_DEEP_RING) + " pipeline=" + std::to_string(SCOPE_PIPELINE) +
+			       " immcoef=" + std::to_string(SCOPE_IMMCOEF) + " ballot=" + std::to_string(SCOPE_BALLOT) + " deep_ring=" + std::to_string(SCOPE_DEEP_RING) + " pipeline=" + std::to_string(SCOPE_PIPELINE) +
 			       " faddr=" + std::to_string(SCOPE_FADDR) + " ldsm=" + std::to_string(SCOPE_LDSM) +
 			       " defer=" + std::to_string(SCOPE_DEFER) + " fast_emit=" + std::to_string(SCOPE_FAST_EMIT);
 	return s.c_str();

@@ -10,7 +10,8 @@
 //              through it, with 4 / 8 / 12 / 16 warps: how well do LSU and issue overlap, and with how many warps?
 // Q3  wide:    64-bit shared atomics (one lane-op updating two adjacent words) - same 16 lanes per clock?
 // Q4  bank:    2- / 4- / 8-way BANK conflicts on distinct words versus k lanes on the SAME word
-// Q5  pipes:   IMAD, PRMT, FFMA-immediate, IDP.4A / IDP.2A issue rates (8 independent chains per thread)
+// Q5  pipes:   IMAD (register and immediate multiplier), PRMT, FFMA-immediate, IDP.4A / IDP.2A issue rates
+//              (8 independent chains per thread)
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -29,7 +30,7 @@ __device__ __forceinline__ void red_add64(uint32_t addr, unsigned long long v)
 }
 
 enum Mode { LANES = 0, MIX_BURST = 1, MIX_SPREAD = 2, WIDE64 = 3, BANK_KWAY = 4, IDP4A = 5, IDP2A = 6, IMAD = 7, ALU_ONLY = 8,
-            SAME_KWAY = 9, ATOM_RET = 10, PRMT = 11, FFMA_IMM = 12 };
+            SAME_KWAY = 9, ATOM_RET = 10, PRMT = 11, FFMA_IMM = 12, IMAD_IMM = 13 };
 
 // One CTA per SM.  `param` = active lanes (LANES), arithmetic instructions per atomic (MIX_*), k (BANK_KWAY).
 template <int MODE, int K = 0>
@@ -113,6 +114,10 @@ __global__ void __launch_bounds__(1024, 1) k2(int iters, int param, uint32_t *si
 #pragma unroll
 			for (int j = 0; j < 8; j++)
 				x[j] = x[j] * a + c;
+		} else if (MODE == IMAD_IMM) {
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				x[j] = x[j] * 439216u + c; // multiplier as an immediate (SCOPE_IMMCOEF's form), addend in a register
 		} else if (MODE == PRMT) {
 #pragma unroll
 			for (int j = 0; j < 8; j++)
@@ -193,6 +198,7 @@ int main()
 	}
 	for (int warps : {4, 8, 16}) {
 		run<IMAD>("imad", warps, 0);
+		run<IMAD_IMM>("imad_immediate_multiplier", warps, 0);
 		run<PRMT>("prmt", warps, 0);
 		run<FFMA_IMM>("ffma_imm", warps, 0);
 		run<IDP4A>("idp4a", warps, 0);
