@@ -110,8 +110,6 @@ struct World {
 	unsigned grid_dim = 0;
 	long steps = 0, progress_mark = 0;
 	const char *error = nullptr;
-	void (*entry)(void *) = nullptr;
-	void *entry_arg = nullptr;
 };
 
 extern World *W;
