@@ -143,7 +143,7 @@ void kernel_entry(bool tma, int colorspace, KernelChoice &k)
 		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
 #if SCOPE_IMMCOEF
 		// the kernels that evaluate the transform exist once per colour space, coefficients as immediates
-		if (!SURF && (VS || SRC == SRC_YUV))
+		if constexpr (!SURF && (VS || SRC == SRC_YUV))
 			k.tma = colorspace == 1 ? scope_strip_kernel_tma<SRC, VS, SURF, 1> : scope_strip_kernel_tma<SRC, VS, SURF, 2>;
 #endif
 		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;

@@ -1465,9 +1465,10 @@ template <int SRC, bool VSCOPE, bool SURFACE>
 constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
 
 // SCOPE_MAXNREG (experiment): an explicit register cap instead of the one ptxas derives from the launch bounds
-// (for 544 threads it stops at 96, not at the 120 that fit: it seems to round the block up to 640 threads)
+// (for 544 threads it stops at 96, not at the 120 that fit: it seems to round the block up to 640 threads);
+// the kernels that run two CTAs per SM keep their 56
 #if defined(SCOPE_MAXNREG) && !defined(SCOPE_EMULATE)
-#define SCOPE_TMA_BOUNDS __maxnreg__(SCOPE_MAXNREG)
+#define SCOPE_TMA_BOUNDS __maxnreg__((kTmaMinCtas<SRC, VSCOPE, SURFACE> == 1 ? SCOPE_MAXNREG : 56))
 #else
 #define SCOPE_TMA_BOUNDS __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
 #endif

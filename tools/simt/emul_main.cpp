@@ -49,7 +49,7 @@ template <int SRC, bool VS, bool SURF> void call_kernel(const Launch &l)
 {
 	if (l.kernel == 0) {
 #if SCOPE_IMMCOEF
-		if (!SURF && (VS || SRC == SRC_YUV)) { // what kernel_entry (csrc/scope_ffi.cu) picks in these builds
+		if constexpr (!SURF && (VS || SRC == SRC_YUV)) { // what kernel_entry (csrc/scope_ffi.cu) picks in these builds
 			if (l.colorspace == 1)
 				scope_strip_kernel_tma<SRC, VS, SURF, 1>(l.P, l.map_rgb, l.map_yuv);
 			else
