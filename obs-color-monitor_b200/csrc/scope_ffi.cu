@@ -117,6 +117,7 @@ struct KernelChoice {
 	TmaKernel tma = nullptr;
 	LdgKernel ldg = nullptr;
 	int smem = 0, threads = 0;
+	int tile_rows = kTileRows; // rows of the TMA box this kernel expects (SCOPE_WIDE_FUSED: per kernel family)
 };
 
 // Which TMA kernel serves the launches: the row-group kernel when the
@@ -126,10 +127,10 @@ bool use_group_kernel()
 {
 	const char *e = getenv("SCOPE_KERNEL");
 	if (e && !strcmp(e, "group"))
-		return true;
+		return !SCOPE_WIDE_FUSED; // (the row-group kernel is not offered in those builds)
 	if (e && !strcmp(e, "tile"))
 		return false;
-	return SCOPE_GROUP_WARPS > 0;
+	return SCOPE_GROUP_WARPS > 0 && !SCOPE_WIDE_FUSED;
 }
 
 template <int SRC, bool VS, bool SURF>
@@ -141,6 +142,7 @@ void kernel_entry(bool tma, int colorspace, KernelChoice &k)
 		k.threads = kGroupWarps * 32 + 32;
 	} else if (tma) {
 		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
+		k.tile_rows = SmemLayout<SRC, VS, SURF, true>::kTileRows;
 #if SCOPE_IMMCOEF
 		// the kernels that evaluate the transform exist once per colour space, coefficients as immediates
 		if constexpr (!SURF && (VS || SRC == SRC_YUV))
@@ -193,12 +195,12 @@ bool pick_kernel(int src, bool vs, bool surface, bool tma, int colorspace, Kerne
 }
 
 int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x_extent_px, uint32_t linesize,
-	     uint32_t height, uint32_t n_frames, size_t frame_stride)
+	     uint32_t height, uint32_t n_frames, size_t frame_stride, int tile_rows)
 {
 	cuuint64_t dims[3] = {x_extent_px, height, n_frames};
 	cuuint64_t strides[2] = {linesize, n_frames > 1 ? (cuuint64_t)frame_stride
 							  : (cuuint64_t)(((size_t)linesize * height + 15) & ~(size_t)15)};
-	cuuint32_t box[3] = {(cuuint32_t)kStripPx, (cuuint32_t)kTileRows, 1};
+	cuuint32_t box[3] = {(cuuint32_t)kStripPx, (cuuint32_t)tile_rows, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
 	const char *l2 = getenv("SCOPE_TMA_L2"); // experiment: SCOPE_TMA_L2=0 turns the L2 promotion off
 	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base16, dims, strides, box, estr,
@@ -297,27 +299,28 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	else if (loader && !strcmp(loader, "ldg"))
 		use_tma = false;
 
+	KernelChoice k;
+	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
+		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
+
 	CUtensorMap map_rgb, map_yuv;
 	memset(&map_rgb, 0, sizeof map_rgb);
 	memset(&map_yuv, 0, sizeof map_yuv);
 	if (use_tma) {
 		if (need_rgb) {
 			int r = make_map(ctx, &map_rgb, rq.rgb - 4u * P.tma_x0_rgb, rq.width + P.tma_x0_rgb, rq.linesize,
-					 rq.height, rq.n_frames, rq.frame_stride);
+					 rq.height, rq.n_frames, rq.frame_stride, k.tile_rows);
 			if (r)
 				return r;
 		}
 		if (need_yuv) {
 			int r = make_map(ctx, &map_yuv, rq.yuv - 4u * P.tma_x0_yuv, rq.width + P.tma_x0_yuv, rq.linesize,
-					 rq.height, rq.n_frames, rq.frame_stride);
+					 rq.height, rq.n_frames, rq.frame_stride, k.tile_rows);
 			if (r)
 				return r;
 		}
 	}
 
-	KernelChoice k;
-	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
-		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
 	const void *fn = use_tma ? (const void *)k.tma : (const void *)k.ldg;
 	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
 

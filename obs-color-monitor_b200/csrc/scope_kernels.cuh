@@ -99,13 +99,23 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_IMMCOEF
 #define SCOPE_IMMCOEF 0
 #endif
+//   SCOPE_WIDE_FUSED (experiment for round 2, OFF) tile geometry per kernel family: the kernels that hold the
+//                 vectorscope (one CTA per SM, 120 registers through __maxnreg__) take tiles of twice the height,
+//                 i.e. 8 rows per warp and visit, the kernels that run two CTAs per SM keep 4 rows (56 registers).
+//                 What `w16n8_immcoef_r120_x` measures for the fused pass, in a form that could ship.
+#ifndef SCOPE_WIDE_FUSED
+#define SCOPE_WIDE_FUSED 0
+#endif
+#if SCOPE_WIDE_FUSED && !defined(SCOPE_MAXNREG)
+#define SCOPE_MAXNREG 120
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
 #ifndef SCOPE_TMA_WARPS
 #define SCOPE_TMA_WARPS 16
 #endif
-constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile
+constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile (SCOPE_WIDE_FUSED: twice that for some kernels, see SmemLayout)
 constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernel (kTileRows / kTmaWarps rows each)
 // SCOPE_GROUP_WARPS > 0 selects the row-group kernel (scope_strip_kernel_tmag) with that many
 // consumer warps for every TMA launch; 0 keeps the tile-synchronous kernel above
@@ -485,6 +495,9 @@ struct SmemLayout {
 	static constexpr int kWave0Off = kVsOff + kVsBytes;
 	static constexpr int kWaveBytes = SRC != SRC_NONE ? 2 * kWaveWords * 4 : 0;
 	static constexpr int kStageOff = kWave0Off + kWaveBytes;
+	// tile height of this kernel family (the two-plane surface-mode ring has no room for taller tiles)
+	static constexpr int kTileRows = (SCOPE_WIDE_FUSED && VSCOPE && kPlanes == 1) ? 2 * scope::kTileRows : scope::kTileRows;
+	static constexpr int kTileBytes = kStripPx * 4 * kTileRows;
 	static constexpr int kStageBytes = USE_TMA ? kPlanes * kTileBytes : 0;
 	// two planes per stage (surface mode) leave room for a 2-deep ring only
 	// as many stages as fit (two planes per stage in surface mode halve the depth)
@@ -1168,7 +1181,7 @@ __device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensor
 					    volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty)
 {
 	constexpr int kStages = L::kStages;
-	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
+	const uint32_t tiles = (P.height + L::kTileRows - 1) / L::kTileRows;
 	uint32_t stage = 0, phase = 0, qw = 0;
 	for (;;) {
 		// guided self-scheduling: take 1/(2 x grid) of what is left (at most chunk_items
@@ -1198,11 +1211,11 @@ __device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensor
 				const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
 				mbar_expect_tx(bar_full + 8 * stage, L::kStageBytes);
 				if (L::kLoadRgb)
-					tma_load_3d(dst, map_rgb, bar_full + 8 * stage, x + (int)P.tma_x0_rgb, (int)(t * kTileRows),
+					tma_load_3d(dst, map_rgb, bar_full + 8 * stage, x + (int)P.tma_x0_rgb, (int)(t * L::kTileRows),
 						    (int)frame);
 				if (L::kLoadYuv)
-					tma_load_3d(dst + (L::kLoadRgb ? kTileBytes : 0), map_yuv, bar_full + 8 * stage,
-						    x + (int)P.tma_x0_yuv, (int)(t * kTileRows), (int)frame);
+					tma_load_3d(dst + (L::kLoadRgb ? L::kTileBytes : 0), map_yuv, bar_full + 8 * stage,
+						    x + (int)P.tma_x0_yuv, (int)(t * L::kTileRows), (int)frame);
 				if (++stage == kStages) {
 					stage = 0;
 					phase ^= 1;
@@ -1225,7 +1238,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	constexpr bool kNeedQ = SURFACE && (R_SRC == SRC_YUV || R_VS);
 	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
 	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
-	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
+	const uint32_t tiles = (P.height + L::kTileRows - 1) / L::kTileRows;
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
 	uint32_t magic; // 0x4B000000 kept in a register so PRMT can take the selector as its immediate
 	magic = opaque_carrier_bias();
@@ -1260,7 +1273,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 			const bool strip_full = strip * kStripPx + kStripPx <= P.width;
 
 			// tiles [0, n_full) lie completely inside the frame (uniform over the CTA)
-			const uint32_t n_full = strip_full ? P.height / kTileRows : 0u;
+			const uint32_t n_full = strip_full ? P.height / L::kTileRows : 0u;
 			bool skip_wait = item == first; // the chunk announcement already waited for tile 0
 			// peek = ask early whether the NEXT tile has landed, so that the answer's latency
 			// hides behind arithmetic instead of stalling the warp at the top of fetch
@@ -1278,7 +1291,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 					if (kNeedP)
 						ldsm_rows<N>(rows, lane, p);
 					if (kNeedQ)
-						ldsm_rows<N>(rows + (L::kLoadRgb ? kTileBytes : 0), lane, q);
+						ldsm_rows<N>(rows + (L::kLoadRgb ? L::kTileBytes : 0), lane, q);
 #pragma unroll
 					for (int k = 0; k < N; k++) {
 						if (!kNeedP)
@@ -1293,7 +1306,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 #pragma unroll
 					for (int k = 0; k < N; k++) {
 						p[k] = kNeedP ? tile[k * kStripPx] : 0u;
-						q[k] = kNeedQ ? tile[k * kStripPx + (L::kLoadRgb ? kTileBytes / 4 : 0)] : 0u;
+						q[k] = kNeedQ ? tile[k * kStripPx + (L::kLoadRgb ? L::kTileBytes / 4 : 0)] : 0u;
 					}
 				}
 				const uint32_t bar = bar_empty + 8 * stage;
@@ -1415,7 +1428,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				bool ok[N];
 				const uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
-				const uint32_t y0 = t * kTileRows + row0;
+				const uint32_t y0 = t * L::kTileRows + row0;
 				if (strip_full && y0 + N <= P.height) {
 					// this warp's rows of the partial tile are all inside the frame
 					Prep<N> E;
@@ -1478,7 +1491,7 @@ __global__ void SCOPE_TMA_BOUNDS
 			       const __grid_constant__ CUtensorMap map_yuv)
 {
 	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
-	constexpr int NW = kTmaWarps, RPW = kTileRows / NW;
+	constexpr int NW = kTmaWarps, RPW = L::kTileRows / NW;
 	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);
@@ -1515,13 +1528,13 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 {
 	constexpr int kStages = L::kStages;
 	constexpr int N = kGroupRows;
-	constexpr uint32_t GPT = kTileRows / kGroupRows; // groups per tile
-	static_assert(kTileRows % kGroupRows == 0, "tile height must be a multiple of the group height");
+	constexpr uint32_t GPT = L::kTileRows / kGroupRows; // groups per tile
+	static_assert(L::kTileRows % kGroupRows == 0, "tile height must be a multiple of the group height");
 	constexpr bool kNeedP = R_SRC == SRC_RGB || (!SURFACE && (R_VS || R_SRC == SRC_YUV));
 	constexpr bool kNeedQ = SURFACE && (R_SRC == SRC_YUV || R_VS);
 	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + L::kVsOff);
 	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + L::kWave0Off);
-	const uint32_t tiles = (P.height + kTileRows - 1) / kTileRows;
+	const uint32_t tiles = (P.height + L::kTileRows - 1) / L::kTileRows;
 	const uint32_t groups = tiles * GPT;          // per strip, including the ones below the frame
 	const uint32_t groups_inside = P.height / N;  // groups [0, groups_inside) have all 4 rows in the frame
 	const uint32_t wave_lane_addr = smem_base + L::kWave0Off + lane * 4;
@@ -1540,7 +1553,7 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 	// "empty" barrier either way (NWORK arrivals complete a phase).  Ahead: tile n - kStages (same
 	// stage, previous phase) was waited for before tile n is asked about.  Behind: tile n + kStages
 	// cannot be loaded before this warp has arrived for tile n, which it does after its wait.
-#ifndef SCOPE_EXPERIMENT
+#if !defined(SCOPE_EXPERIMENT) && !SCOPE_WIDE_FUSED // (the row-group kernel is not offered in those builds)
 	static_assert(NWORK >= (int)GPT, "a warp must own at most one group per tile");
 #endif
 	uint32_t next_tile = 0; // first tile this warp has not finished (read + released, or passed)
@@ -1600,7 +1613,7 @@ __device__ __forceinline__ void tma_consume_groups(const StripParams &P, uint8_t
 				if (kNeedP)
 					ldsm_rows<N>(rows, lane, p);
 				if (kNeedQ)
-					ldsm_rows<N>(rows + (L::kLoadRgb ? kTileBytes : 0), lane, q);
+					ldsm_rows<N>(rows + (L::kLoadRgb ? L::kTileBytes : 0), lane, q);
 #pragma unroll
 				for (int k = 0; k < N; k++) {
 					if (!kNeedP)
@@ -1735,7 +1748,7 @@ __global__ void __launch_bounds__((kSplitVsWarps + kSplitBinWarps) * 32 + 32, 1)
 {
 	using L = SmemLayout<SRC_RGB, true, SURFACE, true>;
 	constexpr int NV = kSplitVsWarps, NB = kSplitBinWarps, NW = NV + NB;
-	constexpr int RV = kTileRows / NV, RB = kTileRows / NB;
+	constexpr int RV = L::kTileRows / NV, RB = L::kTileRows / NB;
 	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);

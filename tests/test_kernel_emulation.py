@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "simt", "_build")
 SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
           [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", "scope_kernels.cuh")]
-VARIANTS = ["default", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "immcoef", "w16n8_straight_immcoef", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+VARIANTS = ["default", "wide", "wide_straight", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "immcoef", "w16n8_straight_immcoef", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
 SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
 K_TMA, K_LDG, K_GROUP = 0, 1, 2
 
@@ -128,20 +128,20 @@ def test_fused_all_scopes_every_variant(emul_libs, oracle, pkg, variant):
         check(oracle, frames, out, yuv, 0x07, 0x07, True, f"{variant} ({lib.emul_build_flags().decode()}) seed {seed}")
 
 
-@pytest.mark.parametrize("variant", ["default", "w8_straight", "w12n6", "immcoef"])
+@pytest.mark.parametrize("variant", ["default", "w8_straight", "w12n6", "immcoef", "wide"])
 def test_other_kernels_and_modes(emul_libs, oracle, pkg, variant):
     lib = emul_libs[variant]
     fr = pkg.frames
     frames = np.stack([fr.alpha_stripes(45, 131, 7), fr.natural(45, 131, 8)])
     yuv = [oracle.rgb_to_yuv(f, 1) for f in frames]
     yuv_arr = np.ascontiguousarray(np.stack(yuv))
-    surface_ok = variant in ("default", "immcoef")   # the _x builds' two-plane ring does not fit (SCOPE_EXPERIMENT)
+    surface_ok = variant in ("default", "immcoef", "wide")   # the _x builds' two-plane ring does not fit (SCOPE_EXPERIMENT)
     cases = [dict(hist_comp=0x70, wave_comp=0x20, vscope=True),                    # fused, YUV bins + vectorscope
              dict(hist_comp=0x07, wave_comp=0x05, vscope=False),                   # no vectorscope: 2 CTAs per SM kernel
              dict(hist_comp=0x00, wave_comp=0x00, vscope=True),                    # vectorscope only
              dict(hist_comp=0x50, wave_comp=0x00, vscope=False)]                   # histogram only, two channels
     for kw in cases:
-        for kernel in (K_TMA, K_LDG) + ((K_GROUP,) if variant == "default" else ()):
+        for kernel in (K_TMA, K_LDG) + ((K_GROUP,) if variant in ("default", "immcoef") else ()):
             out = run(lib, frames, colorspace=1, kernel=kernel, ctas=3, seed=5, **kw)
             check(oracle, frames, out, yuv, kw["hist_comp"], kw["wave_comp"], kw["vscope"], f"{variant} fused {kw} kernel {kernel}")
     if surface_ok:
@@ -155,7 +155,7 @@ def test_other_kernels_and_modes(emul_libs, oracle, pkg, variant):
                       f"{variant} surface {kw} kernel {kernel}")
 
 
-@pytest.mark.parametrize("variant", ["default", "w8", "straight", "rawflat"])
+@pytest.mark.parametrize("variant", ["default", "w8", "straight", "rawflat", "wide_straight"])
 def test_saturation_and_flat_blocks(emul_libs, oracle, pkg, variant):
     """a solid frame: one vectorscope bin takes every pixel (more than the 0x8000 a half-word bin may hold before
     adds are taken back), waveform bins saturate at 255, the flat-block path is the one that runs; plus a frame
@@ -233,7 +233,7 @@ def test_pitched_rows_and_tile_sharded_frames(emul_libs, oracle, pkg, variant):
     assert np.array_equal(np.minimum(acc[0], 255).astype(np.uint8).reshape(256, 256), oracle.vectorscope(y))
 
 
-@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight", "w16n8"])
+@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight", "w16n8", "wide"])
 def test_extreme_geometries(emul_libs, oracle, pkg, variant):
     """one pixel, one row, one column, a narrow tall strip, exactly one tile, one row more than a tile"""
     lib = emul_libs[variant]

@@ -21,6 +21,8 @@ build w8_straight_ballot "-DSCOPE_BALLOT=1 -DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=
 build w16n8 "-DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128" & pids="$pids $!"
 build immcoef "-DSCOPE_IMMCOEF=1" & pids="$pids $!"
 build w16n8_straight_immcoef "-DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_STRAIGHT=1 -DSCOPE_IMMCOEF=1" & pids="$pids $!"
+build wide "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1" & pids="$pids $!"
+build wide_straight "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1" & pids="$pids $!"
 build straight "-DSCOPE_STRAIGHT=1" & pids="$pids $!"
 build w8_straight "-DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8" & pids="$pids $!"
 build rawflat "-DSCOPE_RAWFLAT=1" & pids="$pids $!"

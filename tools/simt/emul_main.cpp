@@ -96,6 +96,16 @@ void thread_entry()
 	swapcontext(&emul::W->cur->ctx, &emul::W->sched);
 }
 
+template <int SRC, bool VS, bool SURF> int tile_rows_total() { return SmemLayout<SRC, VS, SURF, true>::kTileRows; }
+template <bool SURF> int tile_rows_for(int src, bool vs)
+{
+	if (src == SRC_NONE)
+		return tile_rows_total<SRC_NONE, true, SURF>();
+	if (src == SRC_RGB)
+		return vs ? tile_rows_total<SRC_RGB, true, SURF>() : tile_rows_total<SRC_RGB, false, SURF>();
+	return vs ? tile_rows_total<SRC_YUV, true, SURF>() : tile_rows_total<SRC_YUV, false, SURF>();
+}
+
 template <int SRC, bool VS, bool SURF> int smem_total(int kernel)
 {
 	return kernel == 1 ? SmemLayout<SRC, VS, SURF, false>::kTotal : SmemLayout<SRC, VS, SURF, true>::kTotal;
@@ -110,7 +120,7 @@ template <bool SURF> int smem_for(int src, bool vs, int kernel)
 }
 
 void make_map(CUtensorMap &m, const uint8_t *base, uint32_t width, uint32_t linesize, uint32_t height, uint32_t n,
-	      uint64_t frame_stride)
+	      uint64_t frame_stride, int tile_rows)
 {
 	m.base = base;
 	m.dims[0] = width;
@@ -119,7 +129,7 @@ void make_map(CUtensorMap &m, const uint8_t *base, uint32_t width, uint32_t line
 	m.strides[0] = linesize;
 	m.strides[1] = n > 1 ? frame_stride : (((uint64_t)linesize * height + 15) & ~(uint64_t)15);
 	m.box[0] = kStripPx;
-	m.box[1] = kTileRows;
+	m.box[1] = (uint32_t)tile_rows;
 	m.box[2] = 1;
 }
 
@@ -164,10 +174,11 @@ extern "C" int emul_run(EmulRequest *rq)
 
 	const bool need_rgb = !l.surf || l.src == SRC_RGB;
 	const bool need_yuv = l.surf && (l.src == SRC_YUV || l.vs);
+	const int tile_rows = l.surf ? tile_rows_for<true>(l.src, l.vs) : tile_rows_for<false>(l.src, l.vs);
 	if (need_rgb)
-		make_map(l.map_rgb, rq->rgb, rq->width, rq->linesize, rq->height, rq->n_frames, rq->frame_stride);
+		make_map(l.map_rgb, rq->rgb, rq->width, rq->linesize, rq->height, rq->n_frames, rq->frame_stride, tile_rows);
 	if (need_yuv)
-		make_map(l.map_yuv, rq->yuv, rq->width, rq->linesize, rq->height, rq->n_frames, rq->frame_stride);
+		make_map(l.map_yuv, rq->yuv, rq->width, rq->linesize, rq->height, rq->n_frames, rq->frame_stride, tile_rows);
 
 	uint32_t grid = (uint32_t)std::max(1, rq->ctas);
 	if (grid > P.items)
@@ -285,7 +296,7 @@ extern "C" const char *emul_build_flags()
 {
 	static std::string s = std::string("warps=") + std::to_string(kTmaWarps) + " tile_rows=" + std::to_string(kTileRows) +
 			       " straight=" + std::to_string(SCOPE_STRAIGHT) + " rawflat=" + std::to_string(SCOPE_RAWFLAT) +
-			       " immcoef=" + std::to_string(SCOPE_IMMCOEF) + " ballot=" + std::to_string(SCOPE_BALLOT) + " deep_ring=" + std::to_string(SCOPE_DEEP_RING) + " pipeline=" + std::to_string(SCOPE_PIPELINE) +
+			       " wide_fused=" + std::to_string(SCOPE_WIDE_FUSED) + " immcoef=" + std::to_string(SCOPE_IMMCOEF) + " ballot=" + std::to_string(SCOPE_BALLOT) + " deep_ring=" + std::to_string(SCOPE_DEEP_RING) + " pipeline=" + std::to_string(SCOPE_PIPELINE) +
 			       " faddr=" + std::to_string(SCOPE_FADDR) + " ldsm=" + std::to_string(SCOPE_LDSM) +
 			       " defer=" + std::to_string(SCOPE_DEFER) + " fast_emit=" + std::to_string(SCOPE_FAST_EMIT);
 	return s.c_str();

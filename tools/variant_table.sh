@@ -6,7 +6,7 @@ K=scope_strip_kernel_tmaILi1ELb1ELb0
 printf "%-20s %7s %6s %6s %6s %6s %9s %5s %6s\n" build instr alu imad ffma lsu stall/px regs stack
 for lib in obs-color-monitor_b200/lib/libscope_b200.so variants_tmp/*.so; do
   n=$(basename $lib .so); [ "$n" = libscope_b200 ] && n="(in-tree)"
-  KK=$K; case $n in *immcoef*) KK=${K}ELi2;; esac   # SCOPE_IMMCOEF builds: the BT.709 instance
+  KK=$K; case $n in *immcoef*|wide*) KK=${K}ELi2;; esac   # SCOPE_IMMCOEF builds: the BT.709 instance
   out=$(python tools/sass_budget.py $lib --kernel $KK 2>&1)
   tot=$(echo "$out" | sed -n 2p | sed -E 's/.*= ([0-9.]+) per 32 pixels/\1/')
   pw=$(echo "$out" | sed -n 2p | sed -E 's/.*per ([0-9]+) pixel-warps.*/\1/')
