@@ -149,6 +149,28 @@ class CpuReference:
             self.orc.waveform(0x07, f, yuv)
             self.orc.vectorscope(yuv)
 
+    def one_thread(self, budget_s=3.0):
+        """What the reference does in OBS: ONE "color-monitor" worker runs the three loops back to back
+        (roi.c:329-341).  Frames/s of that, and - separately, because the reference gets the YUV plane from
+        its GPU shader - of the oracle's CPU transform.  A few seconds, median of the passes."""
+        def median_fps(fn):
+            times, spent = [], 0.0
+            while spent < budget_s / 2 and len(times) < 20:
+                t0 = time.perf_counter()
+                fn()
+                times.append(time.perf_counter() - t0)
+                spent += times[-1]
+            return 1.0 / sorted(times)[len(times) // 2], len(times)
+        try:
+            loops, n1 = median_fps(lambda: self._work(0))
+            f = self.frames[0][0]
+            yuv, n2 = median_fps(lambda: self.orc.rgb_to_yuv(f, 2))
+            return {"loops_frames_per_s": round(loops, 2), "loops_passes": n1, "yuv_transform_frames_per_s": round(yuv, 2),
+                    "yuv_passes": n2, "note": "one thread, one frame at a time, median; the transform is the oracle's C code "
+                                              "(a GPU shader in the reference) and is not part of any other number here"}
+        except Exception as e:   # context only: never a reason to lose the bench line
+            return {"error": repr(e)[:200]}
+
     def step(self):
         """one pass over the sample; returns seconds"""
         from concurrent.futures import ThreadPoolExecutor
@@ -193,7 +215,8 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "frames_per_step": n * reps, "width": args.width, "height": args.height},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": ref.kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": ref.kind, "sample": sample,
+                         "one_thread": ref.one_thread()},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -331,7 +354,8 @@ def run_b200_arm(args):
         cpu = {"value": ns * passes / spent, "unit": "frames/s", "cores": threads, "kind": ref.kind,
                "sample": f"{passes} passes over {ns} {args.content} {W}x{H} frames ({ns * passes} frames, {spent:.1f} s), "
                          f"the reference's hist RGB + waveform RGB + vectorscope loops, one frame per thread over "
-                         f"{threads} threads, YUV plane precomputed"}
+                         f"{threads} threads, YUV plane precomputed",
+               "one_thread": ref.one_thread()}
 
     if rank == 0:
         line = {
