@@ -90,11 +90,12 @@ def disassemble(lib, kernel):
         if m:
             pending_labels.append(m.group(1))
             continue
-        m = re.match(r'\s*//## File ".*?", line (\d+)', ln)
+        m = re.match(r'\s*//## File "(.*?)", line (\d+)', ln)
         if m:
             if not fresh:
                 chain, fresh = [], True
-            chain.append(int(m.group(1)))
+            # only lines of scope_kernels.cuh carry markers; lines of other files (the experiments header) get 0
+            chain.append(int(m.group(2)) if os.path.basename(m.group(1)) == os.path.basename(SOURCE) else 0)
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);\s*/\* 0x([0-9a-f]{16}) \*/", ln)
         if m:
