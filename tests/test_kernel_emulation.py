@@ -246,3 +246,29 @@ def test_extreme_geometries(emul_libs, oracle, pkg, variant):
                 continue                 # the host sends pitches that are not a multiple of 16 to the plain-load kernel
             out = run(lib, f, kernel=kernel, ctas=2, seed=w + h)
             check(oracle, f, out, yuv, 0x07, 0x07, True, f"{variant} {w}x{h} kernel {kernel}")
+
+
+@pytest.mark.parametrize("case", ["ramp", "random", "solid", "alpha", "natural", "pitched"])
+def test_surface_mode_matches_reference_golden_emulated(emul_libs, case):
+    """The kernels (emulated) against the outputs of the reference's OWN loops - tests/golden/scope_golden.npz, made
+    from the unmodified src/{histogram,waveform,vectorscope}.c - in strict drop-in mode: same planes in, every
+    count and byte equal.  No oracle in between (the GPU twin of this test is in test_gpu_parity.py)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "scope_golden.npz"))
+    rgb, yuv, width = np.ascontiguousarray(g[f"{case}/rgb"]), np.ascontiguousarray(g[f"{case}/yuv"]), int(g[f"{case}/width"])
+    if rgb.ndim == 2:                                   # pitched: (H, linesize) bytes
+        rgb, yuv = rgb.reshape(rgb.shape[0], -1, 4), yuv.reshape(yuv.shape[0], -1, 4)
+    rgb, yuv = rgb[None], yuv[None]
+    for variant in ("default", "wide"):
+        lib = emul_libs[variant]
+        for comp in (0x07, 0x20, 0x50, 0x70, 0x05, 0x42):
+            for kernel in (K_TMA, K_LDG):
+                if kernel == K_TMA and (rgb.shape[2] * 4) % 16:
+                    continue
+                hist, wave, vs, _ = run(lib, rgb, yuv=yuv, surface=True, hist_comp=comp, wave_comp=comp, vscope=True,
+                                        kernel=kernel, ctas=2, seed=comp + kernel, width=width)
+                what = (case, variant, hex(comp), kernel)
+                assert np.array_equal(hist[0].astype(np.float32).view(np.uint32),
+                                      g[f"{case}/hist/{comp:02x}/log0"].view(np.uint32)), what
+                gw = g[f"{case}/wave/{comp:02x}"]
+                assert np.array_equal(wave[0][..., :3], gw[..., :3]) and not wave[0][..., 3].any(), what
+                assert np.array_equal(vs[0], g[f"{case}/vscope"]), what
