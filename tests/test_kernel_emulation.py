@@ -272,3 +272,44 @@ def test_surface_mode_matches_reference_golden_emulated(emul_libs, case):
                 gw = g[f"{case}/wave/{comp:02x}"]
                 assert np.array_equal(wave[0][..., :3], gw[..., :3]) and not wave[0][..., 3].any(), what
                 assert np.array_equal(vs[0], g[f"{case}/vscope"]), what
+
+
+def test_emulator_catches_injected_bugs(oracle, pkg, tmp_path):
+    """The emulation tests must have teeth: a copy of the kernel header with one deliberate bug each - the
+    vectorscope's un-swizzle off by one bit (arithmetic), one arrival too few on the ring's "empty" barriers
+    (protocol), a mailbox of one entry (protocol) - has to FAIL against the oracle or be stopped by the emulator."""
+    import shutil
+    csrc = os.path.join(ROOT, "obs-color-monitor_b200", "csrc")
+    bugs = {
+        "unswizzle": ("return (word & 0xFFu) ^ ((v7 & 7u) << 2);", "return (word & 0xFFu) ^ ((v7 & 3u) << 2);"),
+        "arrivals": ("mbar_init(bar_empty + 8 * s, EMPTY_ARRIVALS);", "mbar_init(bar_empty + 8 * s, EMPTY_ARRIVALS - 1);"),
+        "mailbox": ("constexpr int kQueue = SCOPE_DEEP_RING ? 8 : 4;", "constexpr int kQueue = 1;"),
+    }
+    frames = small_batch(pkg)
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    procs = {}
+    for name, (good, bad) in bugs.items():
+        d = tmp_path / name
+        d.mkdir()
+        for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh"):
+            shutil.copy(os.path.join(csrc, f), d / f)
+        text = (d / "scope_kernels.cuh").read_text()
+        assert text.count(good) == 1, f"the line the '{name}' bug replaces has changed"
+        (d / "scope_kernels.cuh").write_text(text.replace(good, bad))
+        procs[name] = subprocess.Popen(
+            ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DSCOPE_EMULATE", "-include",
+             os.path.join(ROOT, "tools", "simt", "cuda_emul.h"), f"-I{d}", os.path.join(ROOT, "tools", "simt", "emul_main.cpp"),
+             "-o", str(d / "lib.so")])
+    for name, p in procs.items():
+        assert p.wait() == 0
+        lib = C.CDLL(str(tmp_path / name / "lib.so"))
+        lib.emul_run.argtypes = [C.POINTER(Request)]
+        lib.emul_build_flags.restype = C.c_char_p
+        caught = 0
+        for seed, land in ((1, 30), (2, 2), (3, 10)):
+            try:
+                out = run(lib, frames, seed=seed, land=land)
+                check(oracle, frames, out, yuv, 0x07, 0x07, True, name)
+            except AssertionError:
+                caught += 1
+        assert caught > 0, f"injected bug '{name}' went unnoticed"
