@@ -184,9 +184,11 @@ bool pick_kernel(int src, bool vs, bool surface, bool tma, int colorspace, Kerne
 		if (surface) {
 			k.tma = scope_strip_kernel_split<true>;
 			k.smem = SmemLayout<SRC_RGB, true, true, true>::kTotal;
+			k.tile_rows = SmemLayout<SRC_RGB, true, true, true>::kTileRows;
 		} else {
 			k.tma = scope_strip_kernel_split<false>;
 			k.smem = SmemLayout<SRC_RGB, true, false, true>::kTotal;
+			k.tile_rows = SmemLayout<SRC_RGB, true, false, true>::kTileRows;
 		}
 		k.threads = (kSplitVsWarps + kSplitBinWarps) * 32 + 32;
 		return true;
