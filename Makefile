@@ -15,7 +15,7 @@ all: product oracle
 
 product: $(LIBDIR)/libscope_b200.so $(LIBDIR)/libcm_shim.so
 
-$(LIBDIR)/libscope_b200.so: Makefile $(PKG)/csrc/exports.map $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh include/scope_ffi.h
+$(LIBDIR)/libscope_b200.so: Makefile $(PKG)/csrc/exports.map $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
 
@@ -63,7 +63,7 @@ FLAGS_w8_deepring = -DSCOPE_TMA_WARPS=8 -DSCOPE_DEEP_RING=1
 FLAGS_nofaddr = -DSCOPE_FADDR=0
 FLAGS_nodefer = -DSCOPE_DEFER=0
 variants: $(VARIANTS:%=variants_tmp/%.so)
-variants_tmp/%.so: $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh include/scope_ffi.h Makefile
+variants_tmp/%.so: $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h Makefile
 	@mkdir -p variants_tmp
 	$(VARIANT) $(FLAGS_$*) -o $@
 .PHONY: variants

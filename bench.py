@@ -52,6 +52,8 @@ def parse_args():
                     help="batch = the headline (BASELINE config 5 / metric); roi-tiled-8k = config 4; "
                          "stream-vscope-4k = config 3")
     ap.add_argument("--bands", default="rows", choices=["rows", "cols"])
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "peers", "peers-one-shot"],
+                    help="roi-tiled-8k: NCCL all-reduce + clamp, or the fused peer-memory kernel (scope_finalize_peers)")
     ap.add_argument("--scopes", default="hist,wave,vscope",
                     help="subset of hist,wave,vscope for the batch workload (default: all three = the headline)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -490,7 +492,12 @@ def run_roi_tiled(args):
     W, H = 7680, 4320
     eng = pkg.ScopeEngine(local_rank)
     st = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=pkg.COMP_Y, colorspace=args.colorspace)
-    tiled = pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
+    def new_tiled():
+        if args.reduce == "nccl":
+            return pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
+        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=args.bands, two_shot=args.reduce == "peers")
+
+    tiled = new_tiled()
     a, b = tiled.my_band
     # 4 different frames so that successive steps do not hit L2 (8K frame = 133 MB > L2 anyway)
     if args.bands == "rows":
@@ -500,7 +507,7 @@ def run_roi_tiled(args):
         bands = [torch.as_strided(f.reshape(-1)[a * 4:], (H, (W - a) * 4), (W * 4, 1)) for f in full]
 
     # two frames in flight: the all-reduce of frame i overlaps the accumulation of frame i+1
-    tiled2 = pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
+    tiled2 = new_tiled()
     ring = [tiled, tiled2]
     pending = []
 
@@ -549,8 +556,11 @@ def run_roi_tiled(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"BASELINE config 4: one 7680x4320 frame, luma waveform, {args.bands} bands over "
-                                   f"{world} GPU(s), all-reduce of 256x7680 u16x2 pairs ({256 * 7680 * 4 / 1e6:.1f} MB, plane 0 only) "
-                                   f"then saturate", "bands": args.bands},
+                                   f"{world} GPU(s), "
+                                   + ("NCCL all-reduce of 256x7680 u16x2 pairs (%.1f MB, plane 0 only) then saturate" % (256 * 7680 * 4 / 1e6)
+                                      if args.reduce == "nccl" else
+                                      "sum + saturate + distribute in one kernel over NVLink peer memory (%s)" % args.reduce),
+                       "bands": args.bands, "reduce": args.reduce},
             "gpu_launches": eng.launch_count - l0,
             "achieved_read_GBps": args.steps * W * H * 4 / (ms * 1e-3) / 1e9}), flush=True)
     if world > 1:

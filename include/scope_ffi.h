@@ -28,6 +28,11 @@
  *                                    conversion                    src/histogram.c:330-355,397-417
  *   *_intensity / *_display       <- PSDrawBare / PSDrawOverlay    data/vectorscope.effect:27-33,
  *                                                                  data/waveform.effect:30-39
+ *   scope_accumulate_partial() / scope_finalize_partial() / scope_finalize_peers()
+ *                                 <- no counterpart (the reference is single threaded); they keep the
+ *                                    saturating semantics of inc_uint8   src/waveform.c:201-205 and
+ *                                    `if (*c < 255) ++*c`                src/vectorscope.c:233-234
+ *                                    when one frame is split over GPUs: min(sum of partials, 255)
  *
  * Output layouts are byte-for-byte the reference's tex_buf layouts:
  *   histogram    uint32[256][4]   slot 0 = R|V, 1 = G|Y, 2 = B|U, 3 = 0       (histogram.c:379-395)
@@ -184,6 +189,27 @@ int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *params, 
 int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *params, uint32_t full_width,
 			   uint32_t full_height, const struct scope_partial_device *partial,
 			   const struct scope_out_device *out, void *stream);
+
+/* ---- tile-sharded frames without a collective library: reduce + saturate over PEER MEMORY ----
+ * Replaces "NCCL all-reduce of the partials, then scope_finalize_partial" by one kernel.
+ * partials[0..n_partials) are the partial accumulators of ALL ranks, as addresses valid on this
+ * context's device: local allocations or NVLink peer mappings (torch symmetric memory buffer_ptrs,
+ * cudaIpcOpenMemHandle, cudaDeviceEnablePeerAccess ...).  The call sums slice `slice_index` of
+ * `slice_count` of the waveform and vectorscope bins over all partials (16-byte peer loads), saturates
+ * at 255 and stores the u8 images (and the intensity-mapped *_display images, if requested) into
+ * EVERY outs[0..n_outs) - the receiving ranks' output images, again local or peer addresses.
+ *   one-shot : slice 0 of 1, n_outs = 1 (own output): every rank reads everything, no peer stores;
+ *   two-shot : slice = rank of world, outs = all ranks' outputs: 1/N of the reads per rank.
+ * The histogram (4 KB) is always summed whole, into outs[0] only (the LOCAL output), followed by
+ * hist_max like scope_finalize_partial.  All partial and output arrays must be 16-byte aligned.
+ * Synchronisation across ranks is the caller's, on `stream`: every rank's scope_accumulate_partial
+ * must have completed before any rank's kernel reads (a device-side barrier, e.g. the symmetric-memory
+ * handle's barrier()), and in the two-shot form the outputs are complete after a second barrier.
+ * 1 <= n_partials, n_outs <= 16. */
+int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *params, uint32_t full_width,
+			 uint32_t full_height, const struct scope_partial_device *partials, uint32_t n_partials,
+			 uint32_t slice_index, uint32_t slice_count, const struct scope_out_device *outs,
+			 uint32_t n_outs, void *stream);
 
 /* Per-launch device timing of the accumulation kernel (CUDA events recorded on the launch
  * stream around each launch while enabled).  scope_profile_read waits for the recorded

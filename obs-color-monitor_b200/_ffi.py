@@ -25,13 +25,14 @@ SCOPE_HIST, SCOPE_WAVE, SCOPE_VSCOPE, SCOPE_ALL = 1, 2, 4, 7
 COMP_RGB, COMP_Y, COMP_UV, COMP_YUV = 0x07, 0x20, 0x50, 0x70
 MODE_FUSED, MODE_SURFACE = 0, 1
 RING_SLOTS = 3
+MAX_PEERS = 16
 
 # every symbol include/scope_ffi.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = [
     "scope_abi_version", "scope_ctx_create", "scope_ctx_destroy", "scope_last_error",
     "scope_launch_count", "scope_sm_count", "scope_accumulate_host", "scope_submit_host",
     "scope_wait_host", "scope_accumulate_device", "scope_accumulate_partial",
-    "scope_finalize_partial", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table",
+    "scope_finalize_partial", "scope_finalize_peers", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table",
     "scope_wave_bytes", "scope_partial_wave_words", "scope_profile_enable", "scope_profile_read",
 ]
 
@@ -141,6 +142,10 @@ def load() -> C.CDLL:
     L.scope_finalize_partial.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_uint32,
                                          C.POINTER(PartialDevice), C.POINTER(OutDevice), C.c_void_p]
     L.scope_finalize_partial.restype = C.c_int
+    L.scope_finalize_peers.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_uint32,
+                                       C.POINTER(PartialDevice), C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.POINTER(OutDevice), C.c_uint32, C.c_void_p]
+    L.scope_finalize_peers.restype = C.c_int
     L.scope_host_alloc.argtypes = [C.c_size_t]
     L.scope_host_alloc.restype = C.c_void_p
     L.scope_host_free.argtypes = [C.c_void_p]

@@ -5,8 +5,10 @@
 // src/waveform.c:272-289, src/vectorscope.c:248-265) and of the RGB->YUV shader pass
 // (src/common.c:170-221, data/common.effect).  There is no CPU fallback in here.
 #include "scope_kernels.cuh"
+#include "scope_peer_reduce.cuh"
 #include "../../include/scope_ffi.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1016,6 +1018,106 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32
 			CU_TRY(ctx, cudaGetLastError());
 			ctx->launches++;
 		}
+	}
+	return SCOPE_OK;
+}
+
+// Tile-sharded frames without NCCL: the sum over the ranks' partials, the saturation and the
+// distribution of the result in one kernel over peer memory (scope_peer_reduce.cuh).
+int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
+			 const struct scope_partial_device *partials, uint32_t n_partials, uint32_t slice_index,
+			 uint32_t slice_count, const struct scope_out_device *outs, uint32_t n_outs, void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!pr || !partials || !outs)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	if (n_partials == 0 || n_partials > (uint32_t)kMaxPeers || n_outs == 0 || n_outs > (uint32_t)kMaxPeers)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_finalize_peers: 1..16 partials and 1..16 outputs");
+	if (slice_count == 0 || slice_index >= slice_count)
+		return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: slice_index must be < slice_count");
+	if (full_width == 0 || full_height == 0)
+		return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: empty frame");
+	cudaStream_t st = (cudaStream_t)stream;
+
+	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) != 0;
+	const bool want_wave = (pr->scopes & SCOPE_WAVE) != 0;
+	const bool want_hist = (pr->scopes & SCOPE_HIST) != 0 && outs[0].hist_counts;
+	auto misaligned = [](const void *p) { return ((uintptr_t)p & 15u) != 0; };
+
+	PeerReduceParams P;
+	memset(&P, 0, sizeof P);
+	P.n_partials = n_partials;
+	P.n_outs = n_outs;
+	P.n_px = (unsigned long long)256 * full_width;
+	for (uint32_t i = 0; i < n_partials; i++) {
+		P.hist[i] = partials[i].hist_counts;
+		P.pairs[i] = partials[i].wave_pairs;
+		P.vscope[i] = partials[i].vscope_counts;
+		if ((want_hist && !P.hist[i]) || (want_wave && !P.pairs[i]) || (want_vs && !P.vscope[i]))
+			return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: a partial lacks an array a requested scope needs");
+		if (misaligned(P.hist[i]) || misaligned(P.pairs[i]) || misaligned(P.vscope[i]))
+			return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: partial arrays must be 16-byte aligned");
+	}
+	bool any_wave = false, any_vs = false;
+	for (uint32_t r = 0; r < n_outs; r++) {
+		if (want_wave) {
+			P.wave[r] = outs[r].wave;
+			P.wave_display[r] = pr->wave_intensity > 0 ? outs[r].wave_display : nullptr;
+			any_wave = any_wave || P.wave[r] || P.wave_display[r];
+		}
+		if (want_vs) {
+			P.vs_out[r] = outs[r].vscope;
+			P.vs_display[r] = pr->vscope_intensity > 0 ? outs[r].vscope_display : nullptr;
+			any_vs = any_vs || P.vs_out[r] || P.vs_display[r];
+		}
+		if (misaligned(P.wave[r]) || misaligned(P.wave_display[r]) || misaligned(P.vs_out[r]) ||
+		    misaligned(P.vs_display[r]))
+			return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: output images must be 16-byte aligned");
+	}
+	P.wave_intensity = (float)pr->wave_intensity;
+	P.vs_intensity = (float)pr->vscope_intensity;
+	// plane 1 of the pairs only ever holds the R|V channel (scope_partial_device)
+	P.wave_planes = !any_wave ? 0u : (pr->wave_components & 0x44u) ? 2u : 1u;
+
+	// slice k of n over q quads: [k*q/n, (k+1)*q/n)
+	auto slice = [&](unsigned long long quads, uint32_t &q0, uint32_t &q1) {
+		q0 = (uint32_t)(quads * slice_index / slice_count);
+		q1 = (uint32_t)(quads * (slice_index + 1) / slice_count);
+	};
+	const unsigned long long wave_quads = P.n_px / 4;
+	if (wave_quads > 0xFFFFFFFFull)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_finalize_peers: frame too wide");
+	const uint32_t max_blocks = (uint32_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 8u;
+	if (P.wave_planes) {
+		slice(wave_quads, P.wave_q0, P.wave_q1);
+		const uint32_t n = P.wave_q1 - P.wave_q0;
+		P.wave_blocks = n ? std::min((n + 255u) / 256u, max_blocks) : 0u;
+	}
+	if (any_vs) {
+		slice(16384, P.vs_q0, P.vs_q1);
+		const uint32_t n = P.vs_q1 - P.vs_q0;
+		P.vs_blocks = (n + 255u) / 256u;
+	}
+	if (want_hist) {
+		if (misaligned(outs[0].hist_counts))
+			return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: hist_counts must be 16-byte aligned");
+		P.hist_out = outs[0].hist_counts;
+		P.hist_blocks = 1;
+	}
+	const uint32_t grid = P.wave_blocks + P.vs_blocks + P.hist_blocks;
+	if (grid) {
+		peer_reduce_finalize_kernel<<<grid, 256, 0, st>>>(P);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	if (want_hist && outs[0].hist_max && (pr->hist_components & 0x77u)) {
+		hist_max_kernel<<<1, 256, 0, st>>>(outs[0].hist_counts, 1024, outs[0].hist_max, pr->hist_components,
+						    full_width, full_height, pr->level_fixed_value, pr->level_ratio_value);
+		CU_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
 	}
 	return SCOPE_OK;
 }

@@ -278,6 +278,46 @@ class ScopeEngine:
                                                        C.byref(pd), C.byref(od), C.c_void_p(stream)))
         return out
 
+    def finalize_peers(self, partials, outs, *, full_width: int, full_height: int,
+                       settings: Optional[ScopeSettings] = None, slice_index: int = 0, slice_count: int = 1,
+                       stream: Optional[int] = None):
+        """Reduce + saturate over peer memory in one kernel (``scope_finalize_peers``).
+
+        ``partials``: one entry per rank, each a dict like ``alloc_partial`` returns whose values are
+        CUDA tensors **or plain device addresses** (ints: peer mappings such as a symmetric-memory
+        handle's ``buffer_ptrs``).  ``outs``: one dict per receiving rank in the layout of
+        ``alloc_device_out(1, ...)`` (tensors or addresses); ``outs[0]`` is this rank's own output and
+        the only one that receives the histogram.  Cross-rank synchronisation is the caller's."""
+        import torch
+
+        st = settings or ScopeSettings()
+
+        def addr(v):
+            if v is None:
+                return None
+            return v.data_ptr() if hasattr(v, "data_ptr") else int(v)
+
+        pds = (PartialDevice * len(partials))()
+        for i, part in enumerate(partials):
+            pds[i].hist_counts = addr(part.get("hist"))
+            pds[i].wave_pairs = addr(part.get("wave_pairs"))
+            pds[i].vscope_counts = addr(part.get("vscope"))
+        ods = (OutDevice * len(outs))()
+        for i, out in enumerate(outs):
+            ods[i].hist_counts = addr(out.get("hist"))
+            ods[i].hist_max = addr(out.get("hist_max"))
+            ods[i].wave = addr(out.get("wave"))
+            ods[i].vscope = addr(out.get("vscope"))
+            ods[i].wave_display = addr(out.get("wave_display"))
+            ods[i].vscope_display = addr(out.get("vscope_display"))
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        p = st.to_c()
+        self.ctx.check(self.lib.scope_finalize_peers(self.ctx.handle, C.byref(p), full_width, full_height, pds,
+                                                     len(partials), slice_index, slice_count, ods, len(outs),
+                                                     C.c_void_p(stream)))
+        return outs[0]
+
     # test hook
     def debug_yuv_table(self, colorspace: int):
         import torch

@@ -146,3 +146,111 @@ class TiledFrame:
     def reduce_and_finalize(self):
         self.start_reduce()
         return self.finish()
+
+
+class PeerTiledFrame(TiledFrame):
+    """TiledFrame whose cross-rank step is ONE kernel over NVLink peer memory instead of an NCCL all-reduce
+    followed by a clamp (`scope_finalize_peers`, csrc/scope_peer_reduce.cuh).
+
+    The partial accumulators and the u8 result images of every rank live in one symmetric-memory allocation
+    (`torch.distributed._symmetric_memory`: torch only provides the peer mappings and the device-side barrier).
+    `reduce_and_finalize()` = barrier -> kernel -> barrier, all on the current stream:
+
+    * two-shot (default for world > 2): rank r sums slice r of the bins from every peer's partials (16-byte peer
+      loads), saturates and stores the u8 slice into every rank's images (peer stores) - 1/world of the reads;
+    * one-shot: every rank reads all partials and writes only its own images.
+
+    With one rank (or no process group) the same kernel runs on local memory."""
+
+    def __init__(self, engine, full_width: int, full_height: int, settings, mode: str = "rows", group=None,
+                 two_shot: Optional[bool] = None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        assert mode in ("rows", "cols")
+        self.engine, self.settings, self.mode, self.group = engine, settings, mode, group
+        self.width, self.height = full_width, full_height
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bands = row_bands(full_height, self.world) if mode == "rows" else col_bands(full_width, self.world)
+        self.two_shot = (self.world > 2) if two_shot is None else (bool(two_shot) and self.world > 1)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+        # layout of the symmetric allocation, in int32 words; every section starts on a 16-byte boundary
+        W = full_width
+        sections = [("hist", 1024), ("vscope", 65536), ("wave_pairs", 2 * 256 * W),
+                    ("out_wave", 256 * W), ("out_vscope", 65536 // 4)]
+        if settings.wave_intensity > 0:
+            sections.append(("out_wave_display", 256 * W))
+        if settings.vscope_intensity > 0:
+            sections.append(("out_vscope_display", 65536 // 4))
+        self._off, words = {}, 0
+        for name, n in sections:
+            self._off[name] = words
+            words += (n + 3) // 4 * 4
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self._buf = symm_mem.empty(words, dtype=torch.int32, device=dev)
+            self._hdl = symm_mem.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
+            self._bases = [int(p) for p in self._hdl.buffer_ptrs]
+        else:
+            self._buf = torch.empty(words, dtype=torch.int32, device=dev)
+            self._hdl = None
+            self._bases = [self._buf.data_ptr()]
+        self._buf.zero_()
+
+        def view(name, n):
+            return self._buf[self._off[name]:self._off[name] + n]
+
+        self.partial = {"hist": view("hist", 1024), "wave_pairs": view("wave_pairs", 2 * 256 * W).view(2, 256, W),
+                        "vscope": view("vscope", 65536)}
+        # this rank's results, shaped like ScopeEngine.alloc_device_out(1, ...)
+        self.out = engine.alloc_device_out(1, W, settings, dev)
+        if "wave" in self.out:
+            self.out["wave"] = view("out_wave", 256 * W).view(torch.uint8).view(1, 256, W, 4)
+        if "vscope" in self.out:
+            self.out["vscope"] = view("out_vscope", 65536 // 4).view(torch.uint8).view(1, 256, 256)
+        if "wave_display" in self.out:
+            self.out["wave_display"] = view("out_wave_display", 256 * W).view(torch.uint8).view(1, 256, W, 4)
+        if "vscope_display" in self.out:
+            self.out["vscope_display"] = view("out_vscope_display", 65536 // 4).view(torch.uint8).view(1, 256, 256)
+
+    def _addresses(self, rank: int, names) -> Dict[str, int]:
+        return {key: self._bases[rank] + 4 * self._off[sec] for key, sec in names if sec in self._off}
+
+    def reset(self):
+        """zero the partials for the next frame (after reduce_and_finalize's closing barrier nobody reads them)"""
+        for t in self.partial.values():
+            t.zero_()
+
+    def finish(self):
+        """results of the last start_reduce() (everything is stream-ordered; nothing to wait for on the host)"""
+        return self.out
+
+    def reduce_and_finalize(self):
+        self.start_reduce()
+        return self.out
+
+    def start_reduce(self):
+        """Enqueue barrier -> reduce/saturate/distribute kernel -> barrier on the current stream."""
+        part_names = [("hist", "hist"), ("wave_pairs", "wave_pairs"), ("vscope", "vscope")]
+        out_names = [("wave", "out_wave"), ("vscope", "out_vscope"), ("wave_display", "out_wave_display"),
+                     ("vscope_display", "out_vscope_display")]
+        if self._hdl is not None:
+            self._hdl.barrier(channel=0)         # every rank's accumulate_partial is complete and visible
+        partials = [self._addresses(r, part_names) for r in range(self.world)]
+        mine = dict(self._addresses(self.rank, out_names))
+        for k in ("hist", "hist_max"):
+            if k in self.out:
+                mine[k] = self.out[k]
+        mine = {k: v for k, v in mine.items() if k in self.out}
+        outs = [mine]
+        if self.two_shot:
+            outs += [{k: v for k, v in self._addresses(r, out_names).items() if k in self.out}
+                     for r in range(self.world) if r != self.rank]
+        self.engine.finalize_peers(partials, outs, full_width=self.width, full_height=self.height,
+                                   settings=self.settings, slice_index=self.rank if self.two_shot else 0,
+                                   slice_count=self.world if self.two_shot else 1)
+        if self._hdl is not None:
+            self._hdl.barrier(channel=1)         # peers are done reading my partials / writing my images

@@ -62,6 +62,56 @@ def _worker(rank, world, port, q):
     eng.close()
 
 
+def _peer_worker(rank, world, port, q):
+    """PeerTiledFrame over real NVLink peer mappings (torch symmetric memory): one-shot and two-shot must equal
+    the whole frame accumulated on one GPU, for two frames in a row (reset between them)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import obs_color_monitor_b200 as pkg
+    from obs_color_monitor_b200 import frames_torch
+    eng = pkg.ScopeEngine(rank)
+    ok = True
+    w, h = 1000, 700
+    st = pkg.ScopeSettings(vscope_intensity=25)
+    for two_shot in (False, True):
+        tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st, mode="rows", two_shot=two_shot)
+        a, b = tiled.my_band
+        for index in (3, 7):
+            full = frames_torch.mixed_batch(1, w, h, dev, first_index=index, content="natural")[0]
+            whole = eng.accumulate_device(full[None], settings=st)
+            tiled.reset()
+            tiled.accumulate(full[a:b])
+            out = tiled.reduce_and_finalize()
+            torch.cuda.synchronize()
+            for k in ("hist", "hist_max", "wave", "vscope", "vscope_display"):
+                ok = ok and bool(torch.equal(out[k][0], whole[k][0]))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+    eng.close()
+
+
+def test_two_gpus_peer_memory_reduce():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_two_gpus_tiled_and_sharded():
     import torch
     import torch.multiprocessing as mp
