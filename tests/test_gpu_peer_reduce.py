@@ -31,7 +31,8 @@ def _frame(pkg):
 def _check(out, oracle, f, yuv, st):
     want_wave, want_vs = oracle.waveform(st.wave_components, f, yuv), oracle.vectorscope(yuv)
     assert np.array_equal(out["wave"][0].cpu().numpy(), want_wave)
-    assert np.array_equal(out["vscope"][0].cpu().numpy(), want_vs)
+    if "vscope" in out:
+        assert np.array_equal(out["vscope"][0].cpu().numpy(), want_vs)
     if "wave_display" in out:
         assert np.array_equal(out["wave_display"][0].cpu().numpy(), oracle.apply_intensity(want_wave, st.wave_intensity))
     if "vscope_display" in out:
@@ -67,12 +68,14 @@ def test_one_shot_equals_whole_frame_and_finalize_partial(engine, oracle, pkg):
 
 @pytest.mark.parametrize("wave_components", [0x07, 0x20])
 def test_two_shot_every_receiver_complete(engine, oracle, pkg, wave_components):
-    """rank r reduces slice r of 3 and stores into all three receivers; 0x20 (luma only) takes the one-plane path"""
+    """rank r reduces slice r of 3 and stores into all three receivers; 0x20 (luma waveform alone, BASELINE
+    config 4) takes the one-plane path"""
     import torch
     f = _frame(pkg)
     d = torch.from_numpy(f).cuda()
     yuv = oracle.rgb_to_yuv(f, 2)
-    st = pkg.ScopeSettings(wave_components=wave_components)
+    st = pkg.ScopeSettings(wave_components=wave_components,
+                           scopes=pkg.SCOPE_ALL if wave_components == 0x07 else pkg.SCOPE_WAVE)
     parts = _partials(engine, pkg, d, st)
     n = len(parts)
     images = [engine.alloc_device_out(1, W, st) for _ in range(n)]
@@ -86,7 +89,8 @@ def test_two_shot_every_receiver_complete(engine, oracle, pkg, wave_components):
     hist = oracle.histogram_counts(7, f, yuv).ravel()
     for o in images:
         _check(o, oracle, f, yuv, st)
-        assert np.array_equal(o["hist"][0].cpu().numpy().view(np.uint32), hist)
+        if "hist" in o:
+            assert np.array_equal(o["hist"][0].cpu().numpy().view(np.uint32), hist)
 
 
 def test_addresses_instead_of_tensors_and_errors(engine, oracle, pkg):
