@@ -1,4 +1,7 @@
-"""GPU parity of scope_finalize_peers (reduce + saturate over peer memory in one kernel).
+"""(Named _z_ so that it runs after the established GPU suites: it was written when this round's GPU budget was
+already spent and meets the hardware for the first time in the round-end pass.)
+
+GPU parity of scope_finalize_peers (reduce + saturate over peer memory in one kernel).
 On one GPU the "peers" are separate allocations of the same device - the kernel only sees addresses - so the
 arithmetic, the slicing and the stores into several receivers are checked bit-exact against the oracle here;
 tests/test_gpu_multirank.py covers real peer mappings when more than one GPU is visible."""

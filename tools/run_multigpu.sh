@@ -9,7 +9,7 @@ N=${1:-2}
 O=gpurun_out/mg$N; mkdir -p $O
 TR="timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 PORT=29611
-timeout -s KILL 400 python -m pytest -x -q -m gpu tests/test_gpu_multirank.py tests/test_gpu_peer_reduce.py > $O/pytest.full 2>&1
+timeout -s KILL 400 python -m pytest -x -q -m gpu tests/test_gpu_multirank.py tests/test_gpu_z_peer_reduce.py > $O/pytest.full 2>&1
 echo "exit $?" >> $O/pytest.full
 timeout -s KILL 200 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $O/batch_n1.json 2>$O/batch_n1.err
 $TR --master-port $((PORT++)) bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > $O/batch_n$N.json 2>$O/batch_n$N.err
