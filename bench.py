@@ -52,7 +52,7 @@ def parse_args():
                     help="batch = the headline (BASELINE config 5 / metric); roi-tiled-8k = config 4; "
                          "stream-vscope-4k = config 3")
     ap.add_argument("--bands", default="rows", choices=["rows", "cols"])
-    ap.add_argument("--reduce", default="nccl", choices=["nccl", "peers", "peers-one-shot"],
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "peers", "peers-one-shot", "nvls", "nvls-one-shot"],
                     help="roi-tiled-8k: NCCL all-reduce + clamp, or the fused peer-memory kernel (scope_finalize_peers)")
     ap.add_argument("--scopes", default="hist,wave,vscope",
                     help="subset of hist,wave,vscope for the batch workload (default: all three = the headline)")
@@ -495,7 +495,8 @@ def run_roi_tiled(args):
     def new_tiled():
         if args.reduce == "nccl":
             return pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
-        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=args.bands, two_shot=args.reduce == "peers")
+        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=args.bands, two_shot=args.reduce in ("peers", "nvls"),
+                                           nvls=args.reduce.startswith("nvls"))
 
     tiled = new_tiled()
     a, b = tiled.my_band

@@ -28,7 +28,7 @@
  *                                    conversion                    src/histogram.c:330-355,397-417
  *   *_intensity / *_display       <- PSDrawBare / PSDrawOverlay    data/vectorscope.effect:27-33,
  *                                                                  data/waveform.effect:30-39
- *   scope_accumulate_partial() / scope_finalize_partial() / scope_finalize_peers()
+ *   scope_accumulate_partial() / scope_finalize_partial() / scope_finalize_peers() / scope_finalize_multicast()
  *                                 <- no counterpart (the reference is single threaded); they keep the
  *                                    saturating semantics of inc_uint8   src/waveform.c:201-205 and
  *                                    `if (*c < 255) ++*c`                src/vectorscope.c:233-234
@@ -210,6 +210,19 @@ int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *params, uint
 			 uint32_t full_height, const struct scope_partial_device *partials, uint32_t n_partials,
 			 uint32_t slice_index, uint32_t slice_count, const struct scope_out_device *outs,
 			 uint32_t n_outs, void *stream);
+
+/* The same step through the NVSwitch (NVLS): mc_partials holds the MULTICAST addresses of the partial arrays
+ * (one multicast object bound to every rank's buffer: torch symmetric memory's multicast_ptr,
+ * cuMulticastCreate/cuMulticastBindMem).  The kernel reads each bin with multimem.ld_reduce.add - the switch
+ * adds the ranks' copies, one response instead of N - saturates, and
+ *   mc_images == NULL : stores the slice into local_out's images (use slice 0 of 1: every rank gets all);
+ *   mc_images != NULL : stores it with multimem.st to the multicast addresses of the images, i.e. into every
+ *                       rank's images at once (use slice = rank of world).
+ * Histogram and hist_max go to local_out.  Same alignment and synchronisation rules as scope_finalize_peers. */
+int scope_finalize_multicast(scope_ctx *ctx, const struct scope_params *params, uint32_t full_width,
+			     uint32_t full_height, const struct scope_partial_device *mc_partials,
+			     uint32_t slice_index, uint32_t slice_count, const struct scope_out_device *local_out,
+			     const struct scope_out_device *mc_images, void *stream);
 
 /* Per-launch device timing of the accumulation kernel (CUDA events recorded on the launch
  * stream around each launch while enabled).  scope_profile_read waits for the recorded

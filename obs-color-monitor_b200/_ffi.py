@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "scope_abi_version", "scope_ctx_create", "scope_ctx_destroy", "scope_last_error",
     "scope_launch_count", "scope_sm_count", "scope_accumulate_host", "scope_submit_host",
     "scope_wait_host", "scope_accumulate_device", "scope_accumulate_partial",
-    "scope_finalize_partial", "scope_finalize_peers", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table",
+    "scope_finalize_partial", "scope_finalize_peers", "scope_finalize_multicast", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table",
     "scope_wave_bytes", "scope_partial_wave_words", "scope_profile_enable", "scope_profile_read",
 ]
 
@@ -146,6 +146,10 @@ def load() -> C.CDLL:
                                        C.POINTER(PartialDevice), C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.POINTER(OutDevice), C.c_uint32, C.c_void_p]
     L.scope_finalize_peers.restype = C.c_int
+    L.scope_finalize_multicast.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_uint32,
+                                           C.POINTER(PartialDevice), C.c_uint32, C.c_uint32,
+                                           C.POINTER(OutDevice), C.POINTER(OutDevice), C.c_void_p]
+    L.scope_finalize_multicast.restype = C.c_int
     L.scope_host_alloc.argtypes = [C.c_size_t]
     L.scope_host_alloc.restype = C.c_void_p
     L.scope_host_free.argtypes = [C.c_void_p]

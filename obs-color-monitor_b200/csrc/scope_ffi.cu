@@ -1024,16 +1024,14 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32
 
 // Tile-sharded frames without NCCL: the sum over the ranks' partials, the saturation and the
 // distribution of the result in one kernel over peer memory (scope_peer_reduce.cuh).
-int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
-			 const struct scope_partial_device *partials, uint32_t n_partials, uint32_t slice_index,
-			 uint32_t slice_count, const struct scope_out_device *outs, uint32_t n_outs, void *stream)
+namespace {
+// outs[0] is the local output (histogram, hi_max).  images: where the u8 images of the slice go - the same
+// array as outs (peer form) or ONE entry of multicast addresses (multicast_out).
+int finalize_peers_impl(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
+			const struct scope_partial_device *partials, uint32_t n_partials, uint32_t slice_index,
+			uint32_t slice_count, const struct scope_out_device *outs, const struct scope_out_device *images,
+			uint32_t n_outs, void *stream, bool multicast_in, bool multicast_out)
 {
-	if (!ctx)
-		return SCOPE_ERR_INVALID;
-	std::lock_guard<std::mutex> lock(ctx->mu);
-	DeviceGuard guard(ctx->device);
-	if (!pr || !partials || !outs)
-		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
 	if (n_partials == 0 || n_partials > (uint32_t)kMaxPeers || n_outs == 0 || n_outs > (uint32_t)kMaxPeers)
 		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_finalize_peers: 1..16 partials and 1..16 outputs");
 	if (slice_count == 0 || slice_index >= slice_count)
@@ -1051,6 +1049,8 @@ int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t
 	memset(&P, 0, sizeof P);
 	P.n_partials = n_partials;
 	P.n_outs = n_outs;
+	P.multicast = multicast_in ? 1u : 0u;
+	P.multicast_out = multicast_out ? 1u : 0u;
 	P.n_px = (unsigned long long)256 * full_width;
 	for (uint32_t i = 0; i < n_partials; i++) {
 		P.hist[i] = partials[i].hist_counts;
@@ -1064,13 +1064,13 @@ int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t
 	bool any_wave = false, any_vs = false;
 	for (uint32_t r = 0; r < n_outs; r++) {
 		if (want_wave) {
-			P.wave[r] = outs[r].wave;
-			P.wave_display[r] = pr->wave_intensity > 0 ? outs[r].wave_display : nullptr;
+			P.wave[r] = images[r].wave;
+			P.wave_display[r] = pr->wave_intensity > 0 ? images[r].wave_display : nullptr;
 			any_wave = any_wave || P.wave[r] || P.wave_display[r];
 		}
 		if (want_vs) {
-			P.vs_out[r] = outs[r].vscope;
-			P.vs_display[r] = pr->vscope_intensity > 0 ? outs[r].vscope_display : nullptr;
+			P.vs_out[r] = images[r].vscope;
+			P.vs_display[r] = pr->vscope_intensity > 0 ? images[r].vscope_display : nullptr;
 			any_vs = any_vs || P.vs_out[r] || P.vs_display[r];
 		}
 		if (misaligned(P.wave[r]) || misaligned(P.wave_display[r]) || misaligned(P.vs_out[r]) ||
@@ -1120,6 +1120,38 @@ int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t
 		ctx->launches++;
 	}
 	return SCOPE_OK;
+}
+} // namespace
+
+int scope_finalize_peers(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
+			 const struct scope_partial_device *partials, uint32_t n_partials, uint32_t slice_index,
+			 uint32_t slice_count, const struct scope_out_device *outs, uint32_t n_outs, void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!pr || !partials || !outs)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	return finalize_peers_impl(ctx, pr, full_width, full_height, partials, n_partials, slice_index, slice_count, outs,
+				   outs, n_outs, stream, false, false);
+}
+
+// The NVLS form: the NVSwitch sums the ranks' partials (multimem.ld_reduce) and, when mc_images is given,
+// replicates the result slice into every rank's images (multimem.st).
+int scope_finalize_multicast(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
+			     const struct scope_partial_device *mc_partials, uint32_t slice_index, uint32_t slice_count,
+			     const struct scope_out_device *local_out, const struct scope_out_device *mc_images,
+			     void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!pr || !mc_partials || !local_out)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	return finalize_peers_impl(ctx, pr, full_width, full_height, mc_partials, 1, slice_index, slice_count, local_out,
+				   mc_images ? mc_images : local_out, 1, stream, true, mc_images != nullptr);
 }
 
 int scope_profile_enable(scope_ctx *ctx, int on)

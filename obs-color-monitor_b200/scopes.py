@@ -318,6 +318,40 @@ class ScopeEngine:
                                                      C.c_void_p(stream)))
         return outs[0]
 
+    def finalize_multicast(self, mc_partial, local_out, mc_images=None, *, full_width: int, full_height: int,
+                           settings: Optional[ScopeSettings] = None, slice_index: int = 0, slice_count: int = 1,
+                           stream: Optional[int] = None):
+        """The NVLS form (``scope_finalize_multicast``): ``mc_partial`` holds the multicast addresses of the partial
+        arrays, ``mc_images`` (optional) those of the result images; ``local_out`` is this rank's own output."""
+        import torch
+
+        st = settings or ScopeSettings()
+
+        def addr(v):
+            if v is None:
+                return None
+            return v.data_ptr() if hasattr(v, "data_ptr") else int(v)
+
+        pd = PartialDevice()
+        pd.hist_counts, pd.wave_pairs, pd.vscope_counts = (addr(mc_partial.get(k)) for k in ("hist", "wave_pairs", "vscope"))
+
+        def out_struct(d):
+            od = OutDevice()
+            od.hist_counts, od.hist_max = addr(d.get("hist")), addr(d.get("hist_max"))
+            od.wave, od.vscope = addr(d.get("wave")), addr(d.get("vscope"))
+            od.wave_display, od.vscope_display = addr(d.get("wave_display")), addr(d.get("vscope_display"))
+            return od
+
+        lo = out_struct(local_out)
+        mi = out_struct(mc_images) if mc_images is not None else None
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        p = st.to_c()
+        self.ctx.check(self.lib.scope_finalize_multicast(self.ctx.handle, C.byref(p), full_width, full_height,
+                                                         C.byref(pd), slice_index, slice_count, C.byref(lo),
+                                                         C.byref(mi) if mi is not None else None, C.c_void_p(stream)))
+        return local_out
+
     # test hook
     def debug_yuv_table(self, colorspace: int):
         import torch

@@ -160,10 +160,12 @@ class PeerTiledFrame(TiledFrame):
       loads), saturates and stores the u8 slice into every rank's images (peer stores) - 1/world of the reads;
     * one-shot: every rank reads all partials and writes only its own images.
 
+    `nvls=True` lets the NVSwitch do the sum and the distribution (`scope_finalize_multicast`: `multimem.ld_reduce`
+    on the allocation's multicast address, `multimem.st` for the two-shot stores).
     With one rank (or no process group) the same kernel runs on local memory."""
 
     def __init__(self, engine, full_width: int, full_height: int, settings, mode: str = "rows", group=None,
-                 two_shot: Optional[bool] = None, device=None):
+                 two_shot: Optional[bool] = None, device=None, nvls: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -174,6 +176,8 @@ class PeerTiledFrame(TiledFrame):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bands = row_bands(full_height, self.world) if mode == "rows" else col_bands(full_width, self.world)
         self.two_shot = (self.world > 2) if two_shot is None else (bool(two_shot) and self.world > 1)
+        self.nvls = bool(nvls) and self.world > 1
+        self._mc_base = 0
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
 
         # layout of the symmetric allocation, in int32 words; every section starts on a 16-byte boundary
@@ -194,6 +198,11 @@ class PeerTiledFrame(TiledFrame):
             self._buf = symm_mem.empty(words, dtype=torch.int32, device=dev)
             self._hdl = symm_mem.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
             self._bases = [int(p) for p in self._hdl.buffer_ptrs]
+            if nvls:
+                self._mc_base = int(self._hdl.multicast_ptr or 0)
+                if not self._mc_base:
+                    raise RuntimeError("PeerTiledFrame(nvls=True): the symmetric allocation has no multicast mapping "
+                                       "(no NVSwitch multicast support on this system)")
         else:
             self._buf = torch.empty(words, dtype=torch.int32, device=dev)
             self._hdl = None
@@ -245,6 +254,17 @@ class PeerTiledFrame(TiledFrame):
             if k in self.out:
                 mine[k] = self.out[k]
         mine = {k: v for k, v in mine.items() if k in self.out}
+        if self.nvls:
+            # the switch sums (multimem.ld_reduce) and, two-shot, replicates the slice into every rank's images
+            mc = self._mc_base
+            mc_partial = {key: mc + 4 * self._off[sec] for key, sec in part_names}
+            mc_images = ({key: mc + 4 * self._off[sec] for key, sec in out_names if sec in self._off and key in self.out}
+                         if self.two_shot else None)
+            self.engine.finalize_multicast(mc_partial, mine, mc_images, full_width=self.width, full_height=self.height,
+                                           settings=self.settings, slice_index=self.rank if self.two_shot else 0,
+                                           slice_count=self.world if self.two_shot else 1)
+            self._hdl.barrier(channel=1)
+            return
         outs = [mine]
         if self.two_shot:
             outs += [{k: v for k, v in self._addresses(r, out_names).items() if k in self.out}

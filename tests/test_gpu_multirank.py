@@ -78,8 +78,13 @@ def _peer_worker(rank, world, port, q):
     ok = True
     w, h = 1000, 700
     st = pkg.ScopeSettings(vscope_intensity=25)
-    for two_shot in (False, True):
-        tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st, mode="rows", two_shot=two_shot)
+    import torch.distributed._symmetric_memory as symm_mem
+    probe = symm_mem.rendezvous(symm_mem.empty(1024, dtype=torch.int32, device=dev), dist.group.WORLD)
+    forms = [(False, False), (True, False)]
+    if probe.multicast_ptr:                       # the NVLS forms only where the switch offers multicast
+        forms += [(False, True), (True, True)]
+    for two_shot, nvls in forms:
+        tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st, mode="rows", two_shot=two_shot, nvls=nvls)
         a, b = tiled.my_band
         for index in (3, 7):
             full = frames_torch.mixed_batch(1, w, h, dev, first_index=index, content="natural")[0]

@@ -2,7 +2,7 @@
 #   1. the N-GPU tests (NCCL tile sharding, frame sharding, the peer-memory reduce over real NVLink mappings);
 #   2. the headline batch workload at N ranks (frame-sharded, weak scaling) and at 1 rank on the same box;
 #   3. BASELINE config 4 (one 7680x4320 frame, luma waveform, row / column bands) with the three cross-rank
-#      steps: NCCL all-reduce + clamp, the fused peer-memory kernel two-shot and one-shot.
+#      steps: NCCL all-reduce + clamp, the fused peer-memory kernel two-shot and one-shot, and its NVLS form.
 # Everything lands in gpurun_out/mg$N as it finishes.   usage: bash tools/run_multigpu.sh N
 cd $GRAFT_REPO_ROOT
 N=${1:-2}
@@ -15,7 +15,7 @@ timeout -s KILL 200 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-base
 $TR --master-port $((PORT++)) bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > $O/batch_n$N.json 2>$O/batch_n$N.err
 for bands in rows cols; do
   timeout -s KILL 120 python bench.py --workload roi-tiled-8k --bands $bands --steps 200 --warmup 20 > $O/tiled_${bands}_n1.json 2>/dev/null
-  for red in nccl peers peers-one-shot; do
+  for red in nccl peers peers-one-shot nvls nvls-one-shot; do
     $TR --master-port $((PORT++)) bench.py --gpus $N --workload roi-tiled-8k --bands $bands --reduce $red --steps 200 --warmup 20 \
       > $O/tiled_${bands}_${red}_n$N.json 2>$O/tiled_${bands}_${red}_n$N.err
   done
