@@ -185,7 +185,10 @@ def test_peer_tiled_frame_host_logic(host_lib, pkg, oracle, two_shot):
     assert ranks[1].my_band == (110, 220)
     for frame in range(2):                # the second frame checks reset()
         for t, (hist, pairs, vs) in zip(ranks, parts):
+            if frame:
+                assert all(bool(v.any()) for v in t.partial.values())
             t.reset()
+            assert not any(bool(v.any()) for v in t.partial.values())
             t.partial["hist"].copy_(torch.from_numpy(hist))
             t.partial["wave_pairs"].copy_(torch.from_numpy(pairs))
             t.partial["vscope"].copy_(torch.from_numpy(vs))
