@@ -52,6 +52,9 @@ def parse_args():
                     help="batch = the headline (BASELINE config 5 / metric); roi-tiled-8k = config 4; "
                          "stream-vscope-4k = config 3")
     ap.add_argument("--bands", default="rows", choices=["rows", "cols"])
+    ap.add_argument("--graph", action="store_true",
+                    help="roi-tiled-8k: replay each frame's launches (reset, accumulate, cross-rank step) as one CUDA graph, "
+                         "so that the number is the device's and not the Python harness's (not with --reduce nccl at N > 1)")
     ap.add_argument("--reduce", default="nccl", choices=["nccl", "peers", "peers-one-shot", "nvls", "nvls-one-shot"],
                     help="roi-tiled-8k: NCCL all-reduce + clamp, or the fused peer-memory kernel (scope_finalize_peers)")
     ap.add_argument("--scopes", default="hist,wave,vscope",
@@ -537,6 +540,32 @@ def run_roi_tiled(args):
         step(i)
     out = drain()
     barrier()
+    launches_per_frame = None
+    if args.graph:
+        if args.reduce == "nccl" and world > 1:
+            raise SystemExit("--graph needs --reduce peers* / nvls* at N > 1 (the NCCL handles are not captured here)")
+        graphs, outs_g = [], []
+        for i in range(4):
+            g = torch.cuda.CUDAGraph()
+            l_before = eng.launch_count
+            with torch.cuda.graph(g):
+                tiled.reset()
+                tiled.accumulate(bands[i], width=(b - a) if args.bands == "cols" else None)
+                tiled.start_reduce()
+                outs_g.append(tiled.finish())
+            launches_per_frame = eng.launch_count - l_before
+            graphs.append(g)
+
+        def step(i):  # noqa: F811  (replaces the eager step)
+            graphs[i % 4].replay()
+            return outs_g[i % 4]
+
+        def drain():  # noqa: F811
+            return outs_g[(args.steps - 1) % 4]
+
+        for i in range(4):
+            step(i)
+        barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launch_count
     ev0.record()
@@ -562,7 +591,8 @@ def run_roi_tiled(args):
                                       if args.reduce == "nccl" else
                                       "sum + saturate + distribute in one kernel over NVLink peer memory (%s)" % args.reduce),
                        "bands": args.bands, "reduce": args.reduce},
-            "gpu_launches": eng.launch_count - l0,
+            "gpu_launches": (eng.launch_count - l0) if launches_per_frame is None else launches_per_frame * args.steps,
+            "graph": bool(args.graph),
             "achieved_read_GBps": args.steps * W * H * 4 / (ms * 1e-3) / 1e9}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -15,9 +15,13 @@ timeout -s KILL 200 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-base
 $TR --master-port $((PORT++)) bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > $O/batch_n$N.json 2>$O/batch_n$N.err
 for bands in rows cols; do
   timeout -s KILL 120 python bench.py --workload roi-tiled-8k --bands $bands --steps 200 --warmup 20 > $O/tiled_${bands}_n1.json 2>/dev/null
+  timeout -s KILL 120 python bench.py --workload roi-tiled-8k --bands $bands --graph --steps 200 --warmup 20 > $O/tiled_${bands}_graph_n1.json 2>$O/tiled_${bands}_graph_n1.err
   for red in nccl peers peers-one-shot nvls nvls-one-shot; do
     $TR --master-port $((PORT++)) bench.py --gpus $N --workload roi-tiled-8k --bands $bands --reduce $red --steps 200 --warmup 20 \
       > $O/tiled_${bands}_${red}_n$N.json 2>$O/tiled_${bands}_${red}_n$N.err
+    # the same as one CUDA graph per frame: the device's number, without the Python harness's launch overhead
+    [ $red != nccl ] && $TR --master-port $((PORT++)) bench.py --gpus $N --workload roi-tiled-8k --bands $bands --reduce $red --graph \
+      --steps 200 --warmup 20 > $O/tiled_${bands}_${red}_graph_n$N.json 2>$O/tiled_${bands}_${red}_graph_n$N.err
   done
 done
 echo "== pytest"; tail -4 $O/pytest.full
