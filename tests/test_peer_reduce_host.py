@@ -202,3 +202,40 @@ def test_peer_tiled_frame_host_logic(host_lib, pkg, oracle, two_shot):
             assert np.array_equal(out["vscope_display"][0].numpy(), oracle.apply_intensity(want_vs, 25))
             assert np.array_equal(out["hist"][0].numpy().view(np.uint32), oracle.histogram_counts(0x07, f, yuv).ravel())
     assert eng.calls[:3] == ([(0, 3, 3, 3), (1, 3, 3, 3), (2, 3, 3, 3)] if two_shot else [(0, 1, 3, 1)] * 3)
+
+
+def test_random_partials_against_numpy(host_lib):
+    """arbitrary partial arrays (not derived from a frame): u16 halves up to the largest total a frame allows
+    (65535 rows over all ranks), vectorscope and histogram counts up to 2^31 in total; every slicing"""
+    rng = np.random.default_rng(11)
+    for case in range(12):
+        n = int(rng.integers(1, 17))
+        w = int(rng.integers(1, 70))
+        planes = int(rng.integers(1, 3))
+        cap = 65535 // n
+        parts = []
+        for _ in range(n):
+            small = rng.integers(0, 3, size=(2, 256, w, 2)) * rng.integers(0, 200, size=(2, 256, w, 2))
+            big = rng.integers(0, cap + 1, size=(2, 256, w, 2))
+            halves = np.where(rng.random((2, 256, w, 2)) < 0.1, big, small).astype(np.uint32)
+            halves[1, ..., 1] = 0                                   # plane 1 holds R|V only
+            pairs = halves[..., 0] | (halves[..., 1] << 16)
+            vs = (rng.integers(0, 2, size=65536) * rng.integers(0, (2 ** 31) // n, size=65536)).astype(np.uint32)
+            hist = rng.integers(0, (2 ** 31) // n, size=1024).astype(np.uint32)
+            parts.append((_aligned(hist.shape, np.uint32, hist), _aligned(pairs.shape, np.uint32, pairs),
+                          _aligned(vs.shape, np.uint32, vs)))
+        tot = sum(p[1].astype(np.uint64) for p in parts)
+        lo, hi, r = tot[0] & 0xFFFF, tot[0] >> 16, tot[1] & 0xFFFF
+        want = np.zeros((256, w, 4), np.uint8)
+        want[..., 0], want[..., 1] = np.minimum(lo, 255), np.minimum(hi, 255)
+        if planes == 2:
+            want[..., 2] = np.minimum(r, 255)
+        want_vs = np.minimum(sum(p[2].astype(np.uint64) for p in parts), 255).astype(np.uint8).reshape(256, 256)
+        want_hist = sum(p[0].astype(np.uint64) for p in parts).astype(np.uint32)
+        slices = int(rng.integers(1, 6))
+        out, hist_out = _alloc_out(w), _aligned((1024,), np.uint32, 0)
+        for k in range(slices):
+            _run(host_lib, parts, [out], w, planes, True, k, slices, hist_out, max_blocks=int(rng.integers(1, 9)))
+        assert np.array_equal(out["wave"], want), case
+        assert np.array_equal(out["vscope"], want_vs), case
+        assert np.array_equal(hist_out, want_hist), case
