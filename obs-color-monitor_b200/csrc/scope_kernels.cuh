@@ -109,6 +109,16 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #if SCOPE_WIDE_FUSED && !defined(SCOPE_MAXNREG)
 #define SCOPE_MAXNREG 120
 #endif
+//   SCOPE_DEPHASE (experiment for round 2, OFF) the measured time of the fused pass is close to the SUM of its
+//                 issue cycles and its shared-memory cycles: the warps of a CTA start every strip
+//                 together after emit_strip's barrier and then all do arithmetic, then all do atomics.  With this
+//                 flag consumer warps 4-7 and 12-15 begin each strip one arithmetic phase late (one named-barrier
+//                 handshake per strip), so that half the warps issue atomics while the other half computes.  (Bit 2
+//                 of the warp number, not bit 0: warp w runs on scheduler w mod 4, and every scheduler must keep
+//                 warps of both halves or it would sit idle during the other half's arithmetic.)
+#ifndef SCOPE_DEPHASE
+#define SCOPE_DEPHASE 0
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
@@ -769,6 +779,18 @@ __device__ __forceinline__ void workers_bar()
 #endif
 }
 
+// SCOPE_DEPHASE: all NW consumer warps meet here once per strip, the late half (warp & 4) BEFORE their first
+// tile's arithmetic, the others AFTER theirs
+template <int NW>
+__device__ __forceinline__ void dephase_bar()
+{
+#ifdef SCOPE_EMULATE
+	return emul::bar_sync(2, NW * 32);
+#else
+	asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
+#endif
+}
+
 template <int NW>
 __device__ __forceinline__ void zero_bins(uint32_t *vs, uint32_t *wave0, bool vscope, bool bins, int tid)
 {
@@ -1359,7 +1381,16 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 				uint32_t bar = fetch_tile(p, q);
 				release_tile(bar, p, q);
 				peek_tile();
+#if SCOPE_DEPHASE
+				// (n_full is uniform over the CTA: every consumer warp comes through here once per strip)
+				if (warp & 4)
+					dephase_bar<NWORK>();
+#endif
 				prepare_tile<R_SRC, R_VS, SURFACE, N>(tc, coef, p, q, A);
+#if SCOPE_DEPHASE
+				if (!(warp & 4))
+					dephase_bar<NWORK>();
+#endif
 #if SCOPE_STRAIGHT
 				// one step: the atomics of `cur`, the arithmetic of `nxt`.  Ordinary tile: one basic block.
 				auto step = [&](const Prep<N> &cur, Prep<N> &nxt) {
