@@ -36,10 +36,11 @@ clean:
 # instruction budget of a variant's steady-state loop without a GPU.  Names ending in _x are built with
 # SCOPE_EXPERIMENT: their two-plane (surface mode) rings do not fit, run_ab.sh skips those tests for them.
 VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
-VARIANTS = dephase wide_dephase w8_dephase wide wide_straight immcoef w16n8_immcoef_r120_x w16n8_straight_immcoef_r120_x w8 w12n8_x w12n6_x w16n6_x w16n6_straight_x w16n8_r120_x w16n8_straight_r120_x w16n6_straight_r120_x r120 straight w8_straight w12n8_straight_x ballot w8_straight_ballot deepring nopipe rawflat w8_deepring nofaddr nodefer
+VARIANTS = dephase wide_dephase wide_straight_dephase w8_dephase wide wide_straight immcoef w16n8_immcoef_r120_x w16n8_straight_immcoef_r120_x w8 w12n8_x w12n6_x w16n6_x w16n6_straight_x w16n8_r120_x w16n8_straight_r120_x w16n6_straight_r120_x r120 straight w8_straight w12n8_straight_x ballot w8_straight_ballot deepring nopipe rawflat w8_deepring nofaddr nodefer
 FLAGS_w8 = -DSCOPE_TMA_WARPS=8
 FLAGS_dephase = -DSCOPE_DEPHASE=1
 FLAGS_wide_dephase = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_DEPHASE=1
+FLAGS_wide_straight_dephase = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1 -DSCOPE_DEPHASE=1
 FLAGS_w8_dephase = -DSCOPE_TMA_WARPS=8 -DSCOPE_DEPHASE=1
 FLAGS_immcoef = -DSCOPE_IMMCOEF=1
 FLAGS_wide = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1

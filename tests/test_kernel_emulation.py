@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "simt", "_build")
 SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
           [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", f) for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh")]
-VARIANTS = ["default", "dephase", "wide_dephase", "w8_dephase", "wide", "wide_straight", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "immcoef", "w16n8_straight_immcoef", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+VARIANTS = ["default", "dephase", "wide_dephase", "wide_straight_dephase", "w8_dephase", "wide", "wide_straight", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "immcoef", "w16n8_straight_immcoef", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
 SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
 K_TMA, K_LDG, K_GROUP = 0, 1, 2
 

@@ -12,7 +12,7 @@
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/ab; mkdir -p $O
 QUICK=0; [ "$1" = "quick" ] && { QUICK=1; shift; }
-ORDER="dephase wide_dephase wide wide_straight w16n8_immcoef_r120_x w16n8_r120_x w16n8_straight_immcoef_r120_x w16n8_straight_r120_x immcoef w8_straight w12n8_straight_x w8 w12n8_x straight w16n6_straight_r120_x w12n6_x \
+ORDER="dephase wide_dephase wide_straight_dephase wide wide_straight w16n8_immcoef_r120_x w16n8_r120_x w16n8_straight_immcoef_r120_x w16n8_straight_r120_x immcoef w8_straight w12n8_straight_x w8 w12n8_x straight w16n6_straight_r120_x w12n6_x \
        w16n6_straight_x w16n6_x r120 w8_dephase ballot w8_straight_ballot deepring w8_deepring nopipe rawflat nofaddr nodefer"
 [ $# -gt 0 ] && ORDER="$*"
 PT="timeout -s KILL 300 python -m pytest -x -q -m gpu tests"

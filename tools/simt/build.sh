@@ -27,6 +27,7 @@ build straight "-DSCOPE_STRAIGHT=1" & pids="$pids $!"
 build dephase "-DSCOPE_DEPHASE=1" & pids="$pids $!"
 build wide_dephase "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_DEPHASE=1" & pids="$pids $!"
 build w8_dephase "-DSCOPE_TMA_WARPS=8 -DSCOPE_DEPHASE=1" & pids="$pids $!"
+build wide_straight_dephase "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1 -DSCOPE_DEPHASE=1" & pids="$pids $!"
 build w8_straight "-DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8" & pids="$pids $!"
 build rawflat "-DSCOPE_RAWFLAT=1" & pids="$pids $!"
 build deepring "-DSCOPE_DEEP_RING=1" & pids="$pids $!"
