@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--scopes", default="hist,wave,vscope",
                     help="subset of hist,wave,vscope for the batch workload (default: all three = the headline)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config4 sub-record of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -219,13 +220,92 @@ def run_reference_arm(args):
         "impl": "reference", "metric": metric_name(args), "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": n * reps, "width": args.width, "height": args.height},
+        "config": bench_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": ref.kind, "sample": sample,
                          "one_thread": ref.one_thread()},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_config(args, world):
+    """the `config` object of BOTH arms (same keys, same values: it names the workload, not the arm; what the
+    reference arm samples of it is said in its cpu_baseline.sample)"""
+    n, W, H = args.frames_per_gpu, args.width, args.height
+    return {"workload": workload_name(args), "frames_per_gpu": n, "global_batch": n * world, "width": W, "height": H,
+            "parallelism": f"frame-sharded x{world}",
+            "l2": "inputs larger than L2 (batch = %.2f GB per GPU per step)" % (n * W * H * 4 / 1e9)}
+
+
+def check_parity(args, pkg, batch, out, st, n_check=4):
+    """frames 0..n_check-1 of the timed batch: GPU outputs vs the reference's own loops (bit-exact or counted)"""
+    import numpy as np
+    from oracle.oracle import Oracle, Ref
+
+    try:
+        orc = Oracle()
+        ref = Ref() if Ref.available() else None
+        host = batch[:n_check].cpu().numpy()
+        bad, what = 0, []
+        for i in range(n_check):
+            f = np.ascontiguousarray(host[i])
+            yuv = orc.rgb_to_yuv(f, args.colorspace)
+            exp = {}
+            if "hist" in out:
+                exp["hist"] = orc.histogram_counts(0x07, f, yuv).ravel()
+            if "wave" in out:
+                exp["wave"] = (ref.waveform(0x07, f, yuv) if ref else orc.waveform(0x07, f, yuv))
+            if "vscope" in out:
+                exp["vscope"] = (ref.vectorscope(yuv) if ref else orc.vectorscope(yuv))
+            for k, e in exp.items():
+                got = out[k][i].cpu().numpy()
+                got = got.view(np.uint32).ravel() if k == "hist" else got
+                if not np.array_equal(got, np.asarray(e).reshape(got.shape)):
+                    bad += 1
+                    what.append(f"frame {i}: {k}")
+        return {"checked_frames": n_check, "mismatches": bad, "against": "oracle/_ref (the reference's compiled loops)"
+                if ref else "oracle port", "scopes": sorted(k for k in ("hist", "wave", "vscope") if k in out),
+                "detail": what[:8]}
+    except Exception as e:   # context: never a reason to lose the bench line
+        return {"checked_frames": 0, "mismatches": None, "error": repr(e)[:200]}
+
+
+def run_config4_record(args, eng, pkg, dev, world, rank):
+    """the `config4` sub-record of the default line: 8K luma waveform over the ranks, CUDA-graphed per frame.
+    At N > 1: column bands with the strip kernel's own peer stores (the best form) and row bands with the fused
+    peer-memory reduce; if symmetric memory is not available the NCCL forms."""
+    import torch.distributed as dist
+
+    rec = {}
+    plans = [("cols", "peers"), ("rows", "peers")] if world > 1 else [("rows", "peers")]
+    for bands, red in plans:
+        for attempt in (red, "nccl"):
+            try:
+                r = measure_config4(eng, pkg, dev, world, rank, bands=bands, reduce=attempt, graph=True, steps=200,
+                                    warmup=20, colorspace=args.colorspace)
+                err = None
+            except Exception as e:
+                r, err = None, repr(e)[:300]
+            ok = 1 if r is not None else 0
+            if world > 1:
+                import torch
+                flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                ok = int(flag.item())
+            if ok:
+                peak = _hbm_peak()[0]
+                r["roofline"].update({"peak": peak, "frac": r["roofline"]["achieved"] / peak})
+                rec[bands] = r
+                break
+            rec[bands + "_error_" + attempt] = err
+            if attempt == "nccl" or world == 1:
+                break
+    best = max((v for k, v in rec.items() if isinstance(v, dict) and "value" in v), key=lambda v: v["value"], default=None)
+    if best is not None:
+        rec["best"] = {"bands": best["bands"], "reduce": best["reduce"], "value": best["value"],
+                       "ms_per_frame": best["ms_per_frame"]}
+    return rec
 
 
 def metric_name(args):
@@ -286,6 +366,9 @@ def run_b200_arm(args):
         assert bool((hsum == 3 * W * H).all()), "histogram totals are wrong"
     if "vscope" in out:
         assert bool((out["vscope"].amax(dim=(1, 2)) > 0).all())
+    # parity of the TIMED batch (outside the timed region): frames 0..3 = one of every content class of the mixed
+    # batch, bit for bit against the reference's own compiled loops (oracle/_ref; the oracle port if absent)
+    parity = check_parity(args, pkg, batch, out, st, n_check=min(4, n)) if rank == 0 else None
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -346,14 +429,15 @@ def run_b200_arm(args):
         e2e = run_e2e(args, eng, st, batch, dev, world, rank)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         ns = args.cpu_sample_frames or min(threads, 32)
         ref = CpuReference(W, H, ns, threads, args.colorspace, args.content)
         ref.step()
-        # bounded sample: passes over the same ns frames until about 10 s of wall clock are spent
+        # bounded sample: passes over the same ns frames until about 10 s of wall clock are spent (4 s at N > 1,
+        # where the other ranks wait for rank 0)
         spent, passes = 0.0, 0
-        while spent < 10.0 and passes < 1000:
+        while spent < (10.0 if world == 1 else 4.0) and passes < 1000:
             spent += ref.step()
             passes += 1
         cpu = {"value": ns * passes / spent, "unit": "frames/s", "cores": threads, "kind": ref.kind,
@@ -362,16 +446,21 @@ def run_b200_arm(args):
                          f"{threads} threads, YUV plane precomputed",
                "one_thread": ref.one_thread()}
 
+    # ---- BASELINE config 4 on the same ranks (one 8K frame, luma waveform, bands over the GPUs) ----
+    config4 = None
+    if not args.no_config4 and args.workload == "batch":
+        del batch, out
+        torch.cuda.empty_cache()
+        config4 = run_config4_record(args, eng, pkg, dev, world, rank)
+
     if rank == 0:
         line = {
             "metric": metric_name(args), "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_gpu": n, "global_batch": n * world,
-                       "width": W, "height": H, "parallelism": f"frame-sharded x{world}",
-                       "l2": "inputs larger than L2 (batch = %.2f GB per GPU per step)" % (n * W * H * 4 / 1e9)},
-            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "data": "synthetic", "config": bench_config(args, world),
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
+            "e2e": e2e, "config4": config4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -467,23 +556,194 @@ def run_e2e(args, eng, st, batch, dev, world, rank):
             b.synchronize()
             best = max(best, n / (a.elapsed_time(b) * 1e-3) / 1e9)
         per_gpu = out["value"] / world * fbytes / 1e9
-        out["pcie"] = {"h2d_gbs_measured": round(best, 2), "h2d_gbs_used": round(per_gpu, 2),
-                       "frac": round(per_gpu / best, 4),
-                       "how": "256 MiB pinned -> device copy_, best of 5, CUDA events, per GPU, measured alone"}
+        # the same copy on ALL ranks at once (barrier, then 5 back-to-back copies each): what the host side of the
+        # box gives every GPU when N of them pull frames at the same time - the ceiling the N-GPU e2e number has
+        conc = best
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+            b.synchronize()
+            tc = torch.tensor([5 * n / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+            dist.all_reduce(tc, op=dist.ReduceOp.MIN)
+            conc = float(tc.item())
+        out["pcie"] = {"h2d_gbs_measured": round(best, 2), "h2d_gbs_concurrent": round(conc, 2),
+                       "h2d_gbs_used": round(per_gpu, 2), "frac": round(per_gpu / conc, 4),
+                       "frac_of_alone": round(per_gpu / best, 4),
+                       "how": "256 MiB pinned -> device copy_, CUDA events, per GPU: `measured` = best of 5 with this "
+                              "rank copying alone-ish (ranks are not synchronised), `concurrent` = all ranks copying at "
+                              "the same time (min over ranks); frac = used / concurrent"}
     except Exception as e:  # the measurement is context, never a reason to lose the bench line
         out["pcie"] = {"error": repr(e)[:200]}
     return out
 
 
+def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", graph=True, steps=200, warmup=20,
+                    colorspace=2, check=True):
+    """BASELINE config 4: ONE 7680x4320 frame, waveform of luma (components 0x20), split into row bands (or
+    column bands) over the ranks.  A step = one frame; two frames are in flight on two streams (double-buffered
+    accumulators and images), so the cross-rank step of frame i overlaps the accumulation of frame i + 1.
+
+      rows  every rank's strip kernel STORES u16-pair partials for its band (scope_accumulate_band, exclusive: no
+            zero-fill, no atomics), then  nccl: all-reduce + clamp  |  peers / nvls: barrier -> ONE kernel that sums
+            the ranks' partials over NVLink (or in the switch), saturates and stores the u8 image into every rank
+            -> barrier
+      cols  a rank's columns are final: its strip kernel stores them as u8 straight into every rank's image (peer
+            stores; nccl: all-gather of the u8 bands) -> one barrier.  No reduce step at all.
+    Returns a dict (every rank computes it; rank 0 reports)."""
+    import torch
+    import torch.distributed as dist
+
+    from obs_color_monitor_b200 import frames_torch
+
+    W, H = 7680, 4320
+    st = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=pkg.COMP_Y, colorspace=colorspace)
+
+    def new_tiled():
+        if reduce == "nccl":
+            return pkg.sharding.TiledFrame(eng, W, H, st, mode=bands)
+        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=bands, two_shot=reduce in ("peers", "nvls"),
+                                           nvls=reduce.startswith("nvls"))
+
+    ring = [new_tiled(), new_tiled()]
+    a, b = ring[0].my_band
+    # 4 different frames so that successive steps do not hit L2 (an 8K frame is 133 MB > L2; a rank's band of 4
+    # frames is 133 MB at N = 4)
+    if bands == "rows":
+        data = [frames_torch.mixed_batch(1, W, b - a, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
+        width = None
+    else:
+        full = [frames_torch.mixed_batch(1, W, H, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
+        data = [torch.as_strided(f.reshape(-1)[a * 4:], (H, (W - a) * 4), (W * 4, 1)) for f in full]
+        width = b - a
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+
+    def enqueue(j, k):
+        tf = ring[j]
+        tf.reset()
+        tf.accumulate(data[k], width=width)
+        tf.start_reduce()
+        return tf.finish()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    outs = {}
+    for i in range(max(warmup, 4)):
+        with torch.cuda.stream(streams[i % 2]):
+            outs[i % 2] = enqueue(i % 2, i % 4)
+    barrier()
+    parity = None
+    if check:
+        # the last two frames against the unsharded pass on this GPU (which tests/ pins on the oracle at 8K)
+        bad = 0
+        for j, i in ((0, max(warmup, 4) - 2), (1, max(warmup, 4) - 1)):
+            j, k = i % 2, i % 4
+            if bands == "rows":
+                whole_src = frames_torch.mixed_batch(1, W, H, dev, first_index=4 * k + 3, content="natural") \
+                    if world == 1 else None
+            else:
+                whole_src = full[k][None]
+            if whole_src is not None:
+                ref = eng.accumulate_device(whole_src, settings=st)
+                torch.cuda.synchronize()
+                bad += int(not torch.equal(outs[j]["wave"][0], ref["wave"][0]))
+        parity = {"checked_frames": 2 if (bands == "cols" or world == 1) else 0, "mismatches": bad}
+    launches_per_frame, graphs = None, None
+    use_graph = graph and not (reduce == "nccl" and world > 1)
+    graph_error = None
+    if use_graph:
+        try:
+            graphs = {}
+            for j in range(2):
+                for k in range(4):
+                    if (k % 2) != j:
+                        continue
+                    g = torch.cuda.CUDAGraph()
+                    l_before = eng.launch_count
+                    with torch.cuda.graph(g, stream=streams[j]):
+                        enqueue(j, k)
+                    launches_per_frame = eng.launch_count - l_before
+                    graphs[k] = g
+            for i in range(8):
+                with torch.cuda.stream(streams[i % 2]):
+                    graphs[i % 4].replay()
+            barrier()
+        except Exception as e:      # a capture that fails on one rank must not hang the others: fall back together
+            graph_error = repr(e)[:200]
+            use_graph = False
+        if world > 1:
+            flag = torch.tensor([0 if use_graph else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            use_graph = use_graph and int(flag.item()) == 0
+
+    def step(i):
+        with torch.cuda.stream(streams[i % 2]):
+            if use_graph:
+                graphs[i % 4].replay()
+            else:
+                enqueue(i % 2, i % 4)
+
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    join = torch.cuda.Event()
+    l0 = eng.launch_count
+    barrier()
+    cur = torch.cuda.current_stream(dev)
+    ev0.record(cur)
+    for s_ in streams:
+        s_.wait_event(ev0)
+    for i in range(steps):
+        step(i)
+    join.record(streams[1])
+    streams[0].wait_event(join)
+    ev1.record(streams[0])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_bins = 256 * W
+    if world == 1:
+        nvlink = 0
+    elif bands == "cols":
+        nvlink = (world - 1) * n_bins * 4 // world                      # my u8 columns into every other image
+    elif reduce == "nccl":
+        nvlink = 2 * (world - 1) * n_bins * 4 // world                  # ring all-reduce of the u16-pair plane
+    elif reduce in ("peers", "nvls"):
+        nvlink = 2 * (world - 1) * n_bins * 4 // world                  # read my slice of every peer, store it to every peer
+    else:
+        nvlink = (world - 1) * n_bins * 4                               # one-shot: read everything from every peer
+    return {
+        "metric": "frames/sec ROI-tiled waveform (luma) @7680x4320 BGRA", "value": steps / (ms * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 4), "ms_per_frame": ms / steps, "bands": bands,
+        "reduce": reduce if world > 1 else "none (one rank)", "graph": bool(use_graph), "graph_error": graph_error,
+        "frames_in_flight": 2,
+        "bytes_over_nvlink_per_rank_per_frame": int(nvlink),
+        "gpu_launches_per_frame": launches_per_frame if launches_per_frame is not None else (eng.launch_count - l0) / steps,
+        "achieved_read_GBps_all_ranks": steps * W * H * 4 / (ms * 1e-3) / 1e9, "clocks": clocks, "parity": parity,
+        "roofline": {"bound": "hbm", "unit": "GB/s", "note": "per rank: its band's pixel bytes / the frame time",
+                     "achieved": steps * W * H * 4 / world / (ms * 1e-3) / 1e9},
+    }
+
+
 def run_roi_tiled(args):
-    """BASELINE config 4: ONE 7680x4320 frame, waveform of luma (components 0x20), split into row
-    bands (or column bands) over the ranks; partial u16-pair bins all-reduced with NCCL, then
-    saturated.  A step = one frame."""
+    """`--workload roi-tiled-8k`: BASELINE config 4 alone (see measure_config4)."""
     import torch
     import torch.distributed as dist
 
     import obs_color_monitor_b200 as pkg
-    from obs_color_monitor_b200 import frames_torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -492,111 +752,30 @@ def run_roi_tiled(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W, H = 7680, 4320
     eng = pkg.ScopeEngine(local_rank)
-    st = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=pkg.COMP_Y, colorspace=args.colorspace)
-    def new_tiled():
-        if args.reduce == "nccl":
-            return pkg.sharding.TiledFrame(eng, W, H, st, mode=args.bands)
-        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=args.bands, two_shot=args.reduce in ("peers", "nvls"),
-                                           nvls=args.reduce.startswith("nvls"))
-
-    tiled = new_tiled()
-    a, b = tiled.my_band
-    # 4 different frames so that successive steps do not hit L2 (8K frame = 133 MB > L2 anyway)
-    if args.bands == "rows":
-        bands = [frames_torch.mixed_batch(1, W, b - a, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
-    else:
-        full = [frames_torch.mixed_batch(1, W, H, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
-        bands = [torch.as_strided(f.reshape(-1)[a * 4:], (H, (W - a) * 4), (W * 4, 1)) for f in full]
-
-    # two frames in flight: the all-reduce of frame i overlaps the accumulation of frame i+1
-    tiled2 = new_tiled()
-    ring = [tiled, tiled2]
-    pending = []
-
-    def step(i):
-        tf = ring[i % 2]
-        tf.reset()
-        tf.accumulate(bands[i % 4], width=(b - a) if args.bands == "cols" else None)
-        tf.start_reduce()
-        pending.append(tf)
-        if len(pending) > 1:
-            return pending.pop(0).finish()
-        return None
-
-    def drain():
-        out = None
-        while pending:
-            out = pending.pop(0).finish()
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    out = drain()
-    barrier()
-    launches_per_frame = None
-    if args.graph:
-        if args.reduce == "nccl" and world > 1:
-            raise SystemExit("--graph needs --reduce peers* / nvls* at N > 1 (the NCCL handles are not captured here)")
-        graphs, outs_g = [], []
-        for i in range(4):
-            g = torch.cuda.CUDAGraph()
-            l_before = eng.launch_count
-            with torch.cuda.graph(g):
-                tiled.reset()
-                tiled.accumulate(bands[i], width=(b - a) if args.bands == "cols" else None)
-                tiled.start_reduce()
-                outs_g.append(tiled.finish())
-            launches_per_frame = eng.launch_count - l_before
-            graphs.append(g)
-
-        def step(i):  # noqa: F811  (replaces the eager step)
-            graphs[i % 4].replay()
-            return outs_g[i % 4]
-
-        def drain():  # noqa: F811
-            return outs_g[(args.steps - 1) % 4]
-
-        for i in range(4):
-            step(i)
-        barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = eng.launch_count
-    ev0.record()
-    for i in range(args.steps):
-        step(i)
-    out = drain()
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    assert int(out["wave"][0, :, :, 1].to(torch.int64).sum()) > 0
+    res = measure_config4(eng, pkg, dev, world, rank, bands=args.bands, reduce=args.reduce, graph=args.graph,
+                          steps=args.steps, warmup=args.warmup, colorspace=args.colorspace)
     if rank == 0:
-        print(json.dumps({
-            "metric": "frames/sec ROI-tiled waveform (luma) @7680x4320 BGRA", "value": args.steps / (ms * 1e-3),
-            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 4: one 7680x4320 frame, luma waveform, {args.bands} bands over "
-                                   f"{world} GPU(s), "
-                                   + ("NCCL all-reduce of 256x7680 u16x2 pairs (%.1f MB, plane 0 only) then saturate" % (256 * 7680 * 4 / 1e6)
-                                      if args.reduce == "nccl" else
-                                      "sum + saturate + distribute in one kernel over NVLink peer memory (%s)" % args.reduce),
-                       "bands": args.bands, "reduce": args.reduce},
-            "gpu_launches": (eng.launch_count - l0) if launches_per_frame is None else launches_per_frame * args.steps,
-            "graph": bool(args.graph),
-            "achieved_read_GBps": args.steps * W * H * 4 / (ms * 1e-3) / 1e9}), flush=True)
+        peak = _hbm_peak()[0]
+        res["roofline"].update({"peak": peak, "frac": res["roofline"]["achieved"] / peak})
+        res.update({"ms_per_step": res["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "u8", "data": "synthetic",
+                    "config": {"workload": f"BASELINE config 4: one 7680x4320 frame, luma waveform, {args.bands} bands over "
+                                           f"{world} GPU(s), cross-rank step: {res['reduce']}", "bands": args.bands,
+                               "reduce": res["reduce"]},
+                    "gpu_launches": res["gpu_launches_per_frame"] * args.steps})
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
+
+
+def _hbm_peak():
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy, read+write)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
 def run_stream_vscope(args):

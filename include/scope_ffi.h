@@ -156,20 +156,34 @@ uint64_t scope_launch_count(const scope_ctx *ctx);
 int scope_sm_count(const scope_ctx *ctx);
 
 /* ---- host buffers in, host buffers out: the drop-in for the surface callbacks ----
- * Synchronous.  surface pointers are HOST memory, valid only during the call
+ * Synchronous.  surface pointers are HOST memory and only need to be valid during the call
  * (exactly like the mapped stagesurface, common.c:343-372). */
 int scope_accumulate_host(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
 			  const struct scope_out_host *out);
 
 /* ---- 3-deep ring (CM_SURFACE_QUEUE_SIZE, common.h:46) for streams ----
- * scope_submit_host copies the surface into pinned staging slot `slot` (0..2) and
- * enqueues H2D + kernels + D2H on that slot's stream, returning before the GPU
- * finishes; SCOPE_ERR_BUSY if the slot is still in flight (caller drops the frame).
- * scope_wait_host blocks until the slot's results are in `out`. */
+ * scope_submit_host enqueues, on the stream of ring slot `slot` (0..2), the host->device copy of the
+ * surface's planes, the kernels and the device->host copy of the results, and returns before the GPU
+ * finishes; SCOPE_ERR_BUSY if the slot is still in flight (the caller drops the frame, common.c:260-268).
+ * scope_wait_host blocks until the slot's results are in `out`.
+ *
+ * LIFETIME OF THE INPUT (the counterpart of "the mapped stagesurface is valid during the callback",
+ * common.c:343-372): the planes are read by DMA, so
+ *   - page-locked memory (scope_ring_input, scope_host_alloc) is read AFTER the call returns: it must stay
+ *     valid and unmodified until scope_wait_host(slot) has returned.  This is the fast path, one copy;
+ *   - pageable memory is copied to the driver's staging during the call (CUDA's pageable-copy rule) and may be
+ *     reused as soon as the call returns; it is slower.
+ * scope_accumulate_host is submit + wait in one call, so its pointers only need to live for the call.
+ *
+ * scope_ring_input returns the slot's own page-locked input buffer of at least `bytes` bytes - the stand-in
+ * for the reference's stagesurface (gs_stage_texture target, common.c:316-320): the producer stages (or renders)
+ * the frame straight into it and passes pointers into it to scope_submit_host.  SCOPE_ERR_BUSY while the slot
+ * is in flight.  The buffer stays valid until a larger request for the same slot or scope_ctx_destroy. */
 #define SCOPE_RING_SLOTS 3
 int scope_submit_host(scope_ctx *ctx, int slot, const struct scope_params *params,
 		      const struct scope_surface *surface);
 int scope_wait_host(scope_ctx *ctx, int slot, const struct scope_out_host *out);
+int scope_ring_input(scope_ctx *ctx, int slot, size_t bytes, void **out_ptr);
 
 /* ---- device buffers in, device buffers out, batched ----
  * surface pointers are DEVICE memory; frame f lives at pointer + f*frame_stride
@@ -185,6 +199,19 @@ int scope_accumulate_device(scope_ctx *ctx, const struct scope_params *params, c
 int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *tile,
 			     uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
 			     void *stream);
+/* The same with two shortcuts for frames whose bands go to different GPUs:
+ *   flags & SCOPE_BAND_EXCLUSIVE  this call is the ONLY writer of its columns of wave_pairs (a rank accumulates its
+ *       whole row band in one call): the u16 pairs are stored instead of added, so wave_pairs needs no zero-fill and
+ *       no global atomics.  (hist_counts / vscope_counts are still added to: zero them.)
+ *   wave_outs != NULL  the tile spans the FULL HEIGHT of its columns (column bands): its waveform columns are final,
+ *       so they are written as saturated u8 into wave_outs[0 .. n_wave_outs) - this rank's image and, through peer
+ *       mappings, every other rank's - and the waveform needs neither partial sums nor a reduce step: the
+ *       "all-gather" of the column bands is the kernel's own stores (128 bytes per warp and row over NVLink).
+ *       partial may be NULL when only the waveform is requested; 1 <= n_wave_outs <= 16. */
+#define SCOPE_BAND_EXCLUSIVE 1u
+int scope_accumulate_band(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *tile,
+			  uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
+			  uint8_t *const *wave_outs, uint32_t n_wave_outs, uint32_t flags, void *stream);
 /* clamp the (summed) partials into the reference layouts */
 int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *params, uint32_t full_width,
 			   uint32_t full_height, const struct scope_partial_device *partial,

@@ -26,12 +26,13 @@ COMP_RGB, COMP_Y, COMP_UV, COMP_YUV = 0x07, 0x20, 0x50, 0x70
 MODE_FUSED, MODE_SURFACE = 0, 1
 RING_SLOTS = 3
 MAX_PEERS = 16
+BAND_EXCLUSIVE = 1
 
 # every symbol include/scope_ffi.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = [
     "scope_abi_version", "scope_ctx_create", "scope_ctx_destroy", "scope_last_error",
     "scope_launch_count", "scope_sm_count", "scope_accumulate_host", "scope_submit_host",
-    "scope_wait_host", "scope_accumulate_device", "scope_accumulate_partial",
+    "scope_wait_host", "scope_ring_input", "scope_accumulate_device", "scope_accumulate_partial", "scope_accumulate_band",
     "scope_finalize_partial", "scope_finalize_peers", "scope_finalize_multicast", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table",
     "scope_wave_bytes", "scope_partial_wave_words", "scope_profile_enable", "scope_profile_read",
 ]
@@ -133,12 +134,18 @@ def load() -> C.CDLL:
     L.scope_submit_host.restype = C.c_int
     L.scope_wait_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(OutHost)]
     L.scope_wait_host.restype = C.c_int
+    L.scope_ring_input.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.scope_ring_input.restype = C.c_int
     L.scope_accumulate_device.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Surface), C.c_uint32,
                                           C.c_size_t, C.POINTER(OutDevice), C.c_void_p]
     L.scope_accumulate_device.restype = C.c_int
     L.scope_accumulate_partial.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Surface), C.c_uint32,
                                            C.c_uint32, C.POINTER(PartialDevice), C.c_void_p]
     L.scope_accumulate_partial.restype = C.c_int
+    L.scope_accumulate_band.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Surface), C.c_uint32, C.c_uint32,
+                                        C.POINTER(PartialDevice), C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32,
+                                        C.c_void_p]
+    L.scope_accumulate_band.restype = C.c_int
     L.scope_finalize_partial.argtypes = [C.c_void_p, C.POINTER(Params), C.c_uint32, C.c_uint32,
                                          C.POINTER(PartialDevice), C.POINTER(OutDevice), C.c_void_p]
     L.scope_finalize_partial.restype = C.c_int

@@ -42,6 +42,11 @@ struct RingSlot {
 	size_t d_wave_bytes = 0;
 	uint8_t *d_vscope = nullptr;      // 65536
 	uint8_t *d_vscope_disp = nullptr; // 65536
+	uint32_t *d_vs_acc = nullptr;     // 65536 u32: this slot's own vectorscope accumulators (the slots run on
+					  // different streams, so they must not share the context's scratch)
+	// pinned input staging handed out by scope_ring_input() (the "stagesurface" of this slot)
+	uint8_t *h_in = nullptr;
+	size_t h_in_bytes = 0;
 	// pinned result staging
 	uint8_t *h_res = nullptr;
 	size_t h_res_bytes = 0;
@@ -59,11 +64,22 @@ struct scope_ctx {
 	uint64_t launches = 0;
 	PFN_encodeTiled encode = nullptr;
 	bool default_tma = true; // which loader launch_strip prefers when both are possible
-	// scratch u32 vectorscope accumulators [n][65536]
+	// scratch of the DEVICE entry points: u32 vectorscope accumulators [n][65536] and a histogram for
+	// callers that only want hist_max.  One set per context, used by launches on whatever stream the
+	// caller names: `scratch_free` is recorded behind the last kernel that reads them and every new
+	// user waits for it on its own stream first, so two streams never interleave on the scratch.
 	uint32_t *d_vs_acc = nullptr;
 	size_t vs_acc_frames = 0;
 	uint32_t *d_hist_scratch = nullptr;
 	size_t hist_scratch_frames = 0;
+	cudaEvent_t scratch_free = nullptr;
+	bool scratch_used = false;
+	// per-kernel launch facts that never change (cudaFuncSetAttribute done, CTAs per SM)
+	struct KernelFacts {
+		const void *fn;
+		int ctas_per_sm;
+	};
+	std::vector<KernelFacts> kernel_facts;
 	// work counters of the dynamically scheduled launches (one slot per launch, round robin)
 	uint32_t *d_counters = nullptr;
 	uint32_t counter_next = 0;
@@ -122,9 +138,10 @@ struct KernelChoice {
 	int tile_rows = kTileRows; // rows of the TMA box this kernel expects (SCOPE_WIDE_FUSED: per kernel family)
 };
 
-// Which TMA kernel serves the launches: the row-group kernel when the
-// library was built with SCOPE_GROUP_WARPS > 0, unless SCOPE_KERNEL=tile|group says otherwise
-// (kept for A/B runs; both kernels are always compiled in).
+// A/B builds only (-DSCOPE_EXPERIMENT, variants_tmp/): the kernels that were measured and not adopted
+// (scope_kernels_experiments.cuh) and the environment switches that select them.  The shipped
+// library carries neither: it has ONE kernel family and reads no environment variable.
+#ifdef SCOPE_EXPERIMENT
 bool use_group_kernel()
 {
 	const char *e = getenv("SCOPE_KERNEL");
@@ -134,24 +151,28 @@ bool use_group_kernel()
 		return false;
 	return SCOPE_GROUP_WARPS > 0 && !SCOPE_WIDE_FUSED;
 }
+#endif
 
 template <int SRC, bool VS, bool SURF>
 void kernel_entry(bool tma, int colorspace, KernelChoice &k)
 {
+#ifdef SCOPE_EXPERIMENT
 	if (tma && use_group_kernel()) {
 		k.tma = scope_strip_kernel_tmag<SRC, VS, SURF>;
 		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
 		k.threads = kGroupWarps * 32 + 32;
-	} else if (tma) {
-		k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
-		k.tile_rows = SmemLayout<SRC, VS, SURF, true>::kTileRows;
-#if SCOPE_IMMCOEF
-		// the kernels that evaluate the transform exist once per colour space, coefficients as immediates
-		if constexpr (!SURF && (VS || SRC == SRC_YUV))
-			k.tma = colorspace == 1 ? scope_strip_kernel_tma<SRC, VS, SURF, 1> : scope_strip_kernel_tma<SRC, VS, SURF, 2>;
+		return;
+	}
 #endif
+	if (tma) {
+		k.tile_rows = SmemLayout<SRC, VS, SURF, true>::kTileRows;
+		// the kernels that evaluate the transform exist once per colour space, coefficients as immediates
+		if constexpr (SCOPE_IMMCOEF && !SURF && (VS || SRC == SRC_YUV))
+			k.tma = colorspace == 1 ? scope_strip_kernel_tma<SRC, VS, SURF, 1> : scope_strip_kernel_tma<SRC, VS, SURF, 2>;
+		else
+			k.tma = scope_strip_kernel_tma<SRC, VS, SURF>;
 		k.smem = SmemLayout<SRC, VS, SURF, true>::kTotal;
-		k.threads = kTmaWarps * 32 + 32;
+		k.threads = SmemLayout<SRC, VS, SURF, true>::kWarps * 32 + 32;
 	} else {
 		k.ldg = scope_strip_kernel_ldg<SRC, VS, SURF>;
 		k.smem = SmemLayout<SRC, VS, SURF, false>::kTotal;
@@ -179,6 +200,7 @@ bool pick_kernel2(int src, bool vs, bool tma, int colorspace, KernelChoice &k)
 
 bool pick_kernel(int src, bool vs, bool surface, bool tma, int colorspace, KernelChoice &k)
 {
+#ifdef SCOPE_EXPERIMENT
 	// experiment kept for A/B runs (profiles/ubench_r01.md): SCOPE_SPLIT=1 selects the
 	// warp-specialised kernel for the headline combination; it measured no faster
 	const char *split = getenv("SCOPE_SPLIT");
@@ -195,6 +217,7 @@ bool pick_kernel(int src, bool vs, bool surface, bool tma, int colorspace, Kerne
 		k.threads = (kSplitVsWarps + kSplitBinWarps) * 32 + 32;
 		return true;
 	}
+#endif
 	return surface ? pick_kernel2<true>(src, vs, tma, colorspace, k) : pick_kernel2<false>(src, vs, tma, colorspace, k);
 }
 
@@ -206,11 +229,9 @@ int make_map(scope_ctx *ctx, CUtensorMap *map, const uint8_t *base16, uint32_t x
 							  : (cuuint64_t)(((size_t)linesize * height + 15) & ~(size_t)15)};
 	cuuint32_t box[3] = {(cuuint32_t)kStripPx, (cuuint32_t)tile_rows, 1};
 	cuuint32_t estr[3] = {1, 1, 1};
-	const char *l2 = getenv("SCOPE_TMA_L2"); // experiment: SCOPE_TMA_L2=0 turns the L2 promotion off
 	CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base16, dims, strides, box, estr,
 				 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-				 l2 && l2[0] == '0' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-				 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+				 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		char buf[128];
 		snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -236,7 +257,9 @@ struct Request {
 	size_t wave_stride;
 	uint32_t *wave_pairs;
 	uint32_t x_offset, out_width;
-	bool partial;
+	int partial; // StripParams::partial: 0 final u8, 1 add into wave_pairs, 2 store into wave_pairs
+	uint8_t *const *wave_copies = nullptr; // further images that get the final waveform columns (peer stores)
+	uint32_t n_wave_copies = 0;
 	uint32_t *vs_acc;
 	size_t vs_stride;
 };
@@ -269,7 +292,10 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	P.wave_mask = rq.wave_mask;
 	P.x_offset = rq.x_offset;
 	P.out_width = rq.out_width;
-	P.partial = rq.partial ? 1u : 0u;
+	P.partial = (uint32_t)rq.partial;
+	P.n_wave_copies = rq.n_wave_copies;
+	for (uint32_t c = 0; c < rq.n_wave_copies; c++)
+		P.wave_copies[c] = rq.wave_copies[c];
 	P.hist = rq.hist;
 	P.hist_stride = rq.hist_stride;
 	P.wave = rq.wave;
@@ -281,27 +307,27 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 
 	// Loader choice.  TMA can describe the planes if base pointers, pitch and frame stride are
 	// multiples of 16 bytes; everything else (e.g. an ROI crop at an odd column, common.c:272-282)
-	// takes the direct loader.  A map that starts at the pointer rounded down to 16 bytes with
-	// boxes starting 0..3 pixels further right (tma_x0_*) would cover those crops too, but:
-	// SCOPE_LOADER=tma|ldg overrides the default (see DESIGN.md section 4.4 for the measurements).
-	// MEASURED (round 1, gpurun_out/final2/x0_sanitizer.log): sm_100a traps with "Illegal
-	// instruction" inside cp.async.bulk.tensor when the box's first pixel is not 16-byte aligned
-	// in global memory (compute-sanitizer points at tma_load_3d), with or without L2 promotion.
-	// So the x-offset path stays an experiment (SCOPE_TMA_X0=1) and planes whose base is only
-	// pixel-aligned go to the direct loader.
-	const char *x0_env = getenv("SCOPE_TMA_X0");
-	const bool allow_x0 = x0_env && x0_env[0] == '1';
+	// takes the direct loader: sm_100a traps with "Illegal instruction" inside cp.async.bulk.tensor
+	// when a box's first pixel is not 16-byte aligned in global memory, even if the tensor map's base
+	// is (measured in round 1, gpurun_out/final2/x0_sanitizer.log).
 	P.tma_x0_rgb = (uint32_t)(((uintptr_t)rq.rgb & 15u) / 4u);
 	P.tma_x0_yuv = (uint32_t)(((uintptr_t)rq.yuv & 15u) / 4u);
+	bool allow_x0 = false;
+#ifdef SCOPE_EXPERIMENT
+	const char *x0_env = getenv("SCOPE_TMA_X0");
+	allow_x0 = x0_env && x0_env[0] == '1';
+#endif
 	const bool tma_ok = ctx->encode != nullptr && (rq.linesize % 16u) == 0 &&
 			    (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0) &&
 			    (allow_x0 || ((!need_rgb || P.tma_x0_rgb == 0) && (!need_yuv || P.tma_x0_yuv == 0)));
-	const char *loader = getenv("SCOPE_LOADER");
 	bool use_tma = tma_ok && ctx->default_tma;
+#ifdef SCOPE_EXPERIMENT
+	const char *loader = getenv("SCOPE_LOADER"); // A/B builds: SCOPE_LOADER=tma|ldg
 	if (loader && !strcmp(loader, "tma"))
 		use_tma = tma_ok;
 	else if (loader && !strcmp(loader, "ldg"))
 		use_tma = false;
+#endif
 
 	KernelChoice k;
 	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
@@ -325,13 +351,19 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 		}
 	}
 
+	// the opt-in to large dynamic shared memory and the occupancy of a kernel never change: asked once
 	const void *fn = use_tma ? (const void *)k.tma : (const void *)k.ldg;
-	CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
-
-	int ctas_per_sm = 1;
-	CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, k.threads, k.smem));
-	if (ctas_per_sm < 1)
-		return fail(ctx, SCOPE_ERR_CUDA, "kernel does not fit on an SM");
+	int ctas_per_sm = 0;
+	for (const auto &f : ctx->kernel_facts)
+		if (f.fn == fn)
+			ctas_per_sm = f.ctas_per_sm;
+	if (ctas_per_sm == 0) {
+		CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem));
+		CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fn, k.threads, k.smem));
+		if (ctas_per_sm < 1)
+			return fail(ctx, SCOPE_ERR_CUDA, "kernel does not fit on an SM");
+		ctx->kernel_facts.push_back({fn, ctas_per_sm});
+	}
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
 	if (grid > P.items)
 		grid = P.items;
@@ -380,7 +412,7 @@ int ensure_vs_acc(scope_ctx *ctx, size_t frames)
 {
 	if (ctx->vs_acc_frames >= frames)
 		return SCOPE_OK;
-	if (ctx->d_vs_acc)
+	if (ctx->d_vs_acc) // (cudaFree waits for the device, so an earlier user is done before the memory goes away)
 		cudaFree(ctx->d_vs_acc);
 	ctx->d_vs_acc = nullptr;
 	ctx->vs_acc_frames = 0;
@@ -407,8 +439,10 @@ int ensure_hist_scratch(scope_ctx *ctx, size_t frames)
 }
 
 // The whole device-side pass for n frames (used by both the device and the host entry points).
+// slot_vs_acc: a ring slot's own vectorscope accumulators (host entry points, n_frames == 1), or NULL:
+// then the context's shared scratch is used, ordered against its previous user through `scratch_free`.
 int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, uint32_t n_frames,
-	       size_t frame_stride, const scope_out_device *out, cudaStream_t stream)
+	       size_t frame_stride, const scope_out_device *out, cudaStream_t stream, uint32_t *slot_vs_acc = nullptr)
 {
 	if (!pr || !s || !out)
 		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
@@ -432,22 +466,34 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 
 	uint32_t *hist = out->hist_counts;
 	size_t hist_stride = 1024;
+	uint32_t *vs_acc = slot_vs_acc;
+	bool shared_scratch = false;
 	if (want_hist && !hist) {
 		int r = ensure_hist_scratch(ctx, n_frames);
 		if (r)
 			return r;
 		hist = ctx->d_hist_scratch;
+		shared_scratch = true;
+	}
+	if (want_vs && !vs_acc) {
+		int r = ensure_vs_acc(ctx, n_frames);
+		if (r)
+			return r;
+		vs_acc = ctx->d_vs_acc;
+		shared_scratch = true;
+	}
+	if (shared_scratch) {
+		if (!ctx->scratch_free)
+			CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
+		if (ctx->scratch_used) // the previous user (possibly on another stream) must be done with it
+			CU_TRY(ctx, cudaStreamWaitEvent(stream, ctx->scratch_free, 0));
 	}
 	if (want_hist)
 		CU_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)n_frames * 1024 * sizeof(uint32_t), stream));
 	if (want_wave && wsrc == SRC_NONE) // components select no plane: the reference leaves zeros
 		CU_TRY(ctx, cudaMemsetAsync(out->wave, 0, (size_t)n_frames * scope_wave_bytes(s->width), stream));
-	if (want_vs) {
-		int r = ensure_vs_acc(ctx, n_frames);
-		if (r)
-			return r;
-		CU_TRY(ctx, cudaMemsetAsync(ctx->d_vs_acc, 0, (size_t)n_frames * 65536 * sizeof(uint32_t), stream));
-	}
+	if (want_vs)
+		CU_TRY(ctx, cudaMemsetAsync(vs_acc, 0, (size_t)n_frames * 65536 * sizeof(uint32_t), stream));
 
 	Request rq{};
 	rq.rgb = s->rgb_data;
@@ -466,8 +512,8 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	rq.wave_pairs = nullptr;
 	rq.x_offset = 0;
 	rq.out_width = s->width;
-	rq.partial = false;
-	rq.vs_acc = ctx->d_vs_acc;
+	rq.partial = 0;
+	rq.vs_acc = vs_acc;
 	rq.vs_stride = 65536;
 
 	// One launch when histogram and waveform read the same plane (or only one of them is
@@ -507,7 +553,7 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	if (want_vs) {
 		const float k = pr->vscope_intensity > 0 ? (float)pr->vscope_intensity : 1.0f;
 		dim3 grid(65536 / 1024, n_frames);
-		vscope_finalize_kernel<<<grid, 256, 0, stream>>>(ctx->d_vs_acc, 65536, out->vscope,
+		vscope_finalize_kernel<<<grid, 256, 0, stream>>>(vs_acc, 65536, out->vscope,
 								  pr->vscope_intensity > 0 ? out->vscope_display : nullptr,
 								  65536, k);
 		CU_TRY(ctx, cudaGetLastError());
@@ -528,6 +574,10 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 										       (float)pr->wave_intensity);
 		CU_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
+	}
+	if (shared_scratch) {
+		CU_TRY(ctx, cudaEventRecord(ctx->scratch_free, stream));
+		ctx->scratch_used = true;
 	}
 	return SCOPE_OK;
 }
@@ -560,6 +610,7 @@ int ensure_slot(scope_ctx *ctx, RingSlot &sl, size_t in_bytes, uint32_t width)
 		CU_TRY(ctx, cudaMalloc(&sl.d_hist_max, 16));
 		CU_TRY(ctx, cudaMalloc(&sl.d_vscope, 65536));
 		CU_TRY(ctx, cudaMalloc(&sl.d_vscope_disp, 65536));
+		CU_TRY(ctx, cudaMalloc(&sl.d_vs_acc, 65536 * sizeof(uint32_t)));
 	}
 	if (sl.d_in_bytes < in_bytes) {
 		if (sl.d_in)
@@ -651,7 +702,7 @@ int submit_host(scope_ctx *ctx, int slot, const scope_params *pr, const scope_su
 	od.wave_display = pr->wave_intensity > 0 ? sl.d_wave_disp : nullptr;
 	od.vscope = sl.d_vscope;
 	od.vscope_display = pr->vscope_intensity > 0 ? sl.d_vscope_disp : nullptr;
-	r = run_device(ctx, pr, &ds, 1, plane_bytes, &od, sl.stream);
+	r = run_device(ctx, pr, &ds, 1, plane_bytes, &od, sl.stream, sl.d_vs_acc);
 	if (r)
 		return r;
 
@@ -824,6 +875,9 @@ void scope_ctx_destroy(scope_ctx *ctx)
 		cudaFree(sl.d_wave_disp);
 		cudaFree(sl.d_vscope);
 		cudaFree(sl.d_vscope_disp);
+		cudaFree(sl.d_vs_acc);
+		if (sl.h_in)
+			cudaFreeHost(sl.h_in);
 		if (sl.h_res)
 			cudaFreeHost(sl.h_res);
 		if (sl.done)
@@ -834,6 +888,8 @@ void scope_ctx_destroy(scope_ctx *ctx)
 	cudaFree(ctx->d_vs_acc);
 	cudaFree(ctx->d_hist_scratch);
 	cudaFree(ctx->d_counters);
+	if (ctx->scratch_free)
+		cudaEventDestroy(ctx->scratch_free);
 	for (auto &ev : ctx->prof_events)
 		ctx->prof_pool.push_back(ev);
 	for (auto &ev : ctx->prof_pool) {
@@ -886,6 +942,32 @@ int scope_wait_host(scope_ctx *ctx, int slot, const struct scope_out_host *out)
 	return wait_host(ctx, slot, out);
 }
 
+int scope_ring_input(scope_ctx *ctx, int slot, size_t bytes, void **out_ptr)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!out_ptr || slot < 0 || slot >= SCOPE_RING_SLOTS)
+		return fail(ctx, SCOPE_ERR_INVALID, "scope_ring_input: bad slot or NULL out_ptr");
+	*out_ptr = nullptr;
+	RingSlot &sl = ctx->ring[slot];
+	if (sl.in_flight) // the DMA of the submission in flight may still be reading the buffer
+		return fail(ctx, SCOPE_ERR_BUSY, "ring slot still in flight");
+	if (sl.h_in_bytes < bytes) {
+		if (sl.h_in)
+			cudaFreeHost(sl.h_in);
+		sl.h_in = nullptr;
+		sl.h_in_bytes = 0;
+		cudaError_t e = cudaHostAlloc(&sl.h_in, bytes ? bytes : 1, cudaHostAllocDefault);
+		if (e != cudaSuccess)
+			return fail(ctx, SCOPE_ERR_NOMEM, "cudaHostAlloc(input staging)", e);
+		sl.h_in_bytes = bytes;
+	}
+	*out_ptr = sl.h_in;
+	return SCOPE_OK;
+}
+
 int scope_accumulate_host(scope_ctx *ctx, const struct scope_params *params, const struct scope_surface *surface,
 			  const struct scope_out_host *out)
 {
@@ -908,22 +990,24 @@ int scope_accumulate_host(scope_ctx *ctx, const struct scope_params *params, con
 	return wait_host(ctx, slot, out);
 }
 
-int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *pr, const struct scope_surface *tile,
-			     uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
-			     void *stream)
+namespace {
+// One band of a tile-sharded frame.  wave_outs == NULL: the waveform goes into partial->wave_pairs (u16 pairs, added,
+// or stored when `exclusive`).  wave_outs != NULL: the band spans the full height of its columns, so its waveform
+// columns are final: written as saturated u8 into every wave_outs[i] (local and peer images), no partial, no reduce.
+int accumulate_band(scope_ctx *ctx, const struct scope_params *pr, const struct scope_surface *tile, uint32_t x_offset,
+		    uint32_t full_width, const struct scope_partial_device *partial, uint8_t *const *wave_outs,
+		    uint32_t n_wave_outs, bool exclusive, cudaStream_t st)
 {
-	if (!ctx)
-		return SCOPE_ERR_INVALID;
-	std::lock_guard<std::mutex> lock(ctx->mu);
-	DeviceGuard guard(ctx->device);
-	if (!pr || !tile || !partial)
+	if (!pr || !tile || (!partial && !wave_outs))
 		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
 	if (tile->width == 0 || tile->height == 0 || x_offset + tile->width > full_width)
 		return fail(ctx, SCOPE_ERR_INVALID, "bad tile geometry");
+	if (wave_outs && (n_wave_outs == 0 || n_wave_outs > (uint32_t)kMaxWaveCopies + 1u))
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_accumulate_band: 1..16 waveform outputs");
 	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
-	const bool want_hist = (pr->scopes & SCOPE_HIST) && partial->hist_counts;
-	const bool want_wave = (pr->scopes & SCOPE_WAVE) && partial->wave_pairs;
-	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) && partial->vscope_counts;
+	const bool want_hist = (pr->scopes & SCOPE_HIST) && partial && partial->hist_counts;
+	const bool want_wave = (pr->scopes & SCOPE_WAVE) && (wave_outs ? wave_outs[0] != nullptr : (partial && partial->wave_pairs));
+	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) && partial && partial->vscope_counts;
 	int hsrc = SRC_NONE, wsrc = SRC_NONE;
 	uint32_t hmask = 0, wmask = 0;
 	if (want_hist)
@@ -940,17 +1024,26 @@ int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *pr, cons
 	rq.frame_stride = 0;
 	rq.colorspace = tile->colorspace;
 	rq.surface = surface;
-	rq.hist = partial->hist_counts;
+	rq.hist = partial ? partial->hist_counts : nullptr;
 	rq.hist_stride = 1024;
-	rq.wave = nullptr;
-	rq.wave_stride = 0;
-	rq.wave_pairs = partial->wave_pairs;
 	rq.x_offset = x_offset;
 	rq.out_width = full_width;
-	rq.partial = true;
-	rq.vs_acc = partial->vscope_counts;
+	if (wave_outs) {
+		rq.wave = wave_outs[0];
+		rq.wave_stride = scope_wave_bytes(full_width);
+		rq.wave_copies = wave_outs + 1;
+		rq.n_wave_copies = n_wave_outs - 1;
+		rq.partial = 0;
+		if (want_wave && wsrc == SRC_NONE) // components select no plane: the reference leaves zeros
+			return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_accumulate_band: wave_components select no plane");
+	} else {
+		rq.wave = nullptr;
+		rq.wave_stride = 0;
+		rq.wave_pairs = partial->wave_pairs;
+		rq.partial = exclusive ? 2 : 1;
+	}
+	rq.vs_acc = partial ? partial->vscope_counts : nullptr;
 	rq.vs_stride = 65536;
-	cudaStream_t st = (cudaStream_t)stream;
 	if (hsrc != SRC_NONE && wsrc != SRC_NONE && hsrc != wsrc) {
 		Request a = rq;
 		a.src = wsrc;
@@ -975,6 +1068,32 @@ int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *pr, cons
 	a.vscope = want_vs;
 	return launch_strip(ctx, a, st);
 }
+} // namespace
+
+int scope_accumulate_partial(scope_ctx *ctx, const struct scope_params *pr, const struct scope_surface *tile,
+			     uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
+			     void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (!partial)
+		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	return accumulate_band(ctx, pr, tile, x_offset, full_width, partial, nullptr, 0, false, (cudaStream_t)stream);
+}
+
+int scope_accumulate_band(scope_ctx *ctx, const struct scope_params *pr, const struct scope_surface *tile,
+			  uint32_t x_offset, uint32_t full_width, const struct scope_partial_device *partial,
+			  uint8_t *const *wave_outs, uint32_t n_wave_outs, uint32_t flags, void *stream)
+{
+	if (!ctx)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	return accumulate_band(ctx, pr, tile, x_offset, full_width, partial, wave_outs, n_wave_outs,
+			       (flags & SCOPE_BAND_EXCLUSIVE) != 0, (cudaStream_t)stream);
+}
 
 int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32_t full_width, uint32_t full_height,
 			   const struct scope_partial_device *partial, const struct scope_out_device *out, void *stream)
@@ -985,6 +1104,10 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32
 	DeviceGuard guard(ctx->device);
 	if (!pr || !partial || !out)
 		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
+	// the summed u16 halves of wave_pairs count up to full_height: a taller frame would carry from the
+	// B|U half into the G|Y half
+	if (full_height > 65535u)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "full_height > 65535 (u16 halves of the partial waveform)");
 	cudaStream_t st = (cudaStream_t)stream;
 	if ((pr->scopes & SCOPE_VSCOPE) && partial->vscope_counts && (out->vscope || out->vscope_display)) {
 		const float k = pr->vscope_intensity > 0 ? (float)pr->vscope_intensity : 1.0f;
@@ -996,8 +1119,9 @@ int scope_finalize_partial(scope_ctx *ctx, const struct scope_params *pr, uint32
 	}
 	if ((pr->scopes & SCOPE_WAVE) && partial->wave_pairs && out->wave) {
 		const size_t n_px = (size_t)256 * full_width;
-		wave_pairs_finalize_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(partial->wave_pairs, out->wave,
-											      n_px);
+		// plane 1 only ever holds the R|V channel: without it the plane need not even be reduced (scope_ffi.h)
+		wave_pairs_finalize_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, st>>>(
+			partial->wave_pairs, out->wave, n_px, (pr->wave_components & 0x44u) ? 1 : 0);
 		CU_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 		if (out->wave_display && pr->wave_intensity > 0) {
@@ -1038,6 +1162,8 @@ int finalize_peers_impl(scope_ctx *ctx, const struct scope_params *pr, uint32_t 
 		return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: slice_index must be < slice_count");
 	if (full_width == 0 || full_height == 0)
 		return fail(ctx, SCOPE_ERR_INVALID, "scope_finalize_peers: empty frame");
+	if (full_height > 65535u)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_finalize_peers: full_height > 65535 (u16 halves of the partial waveform)");
 	cudaStream_t st = (cudaStream_t)stream;
 
 	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) != 0;

@@ -93,11 +93,12 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_BALLOT
 #define SCOPE_BALLOT 0
 #endif
-//   SCOPE_IMMCOEF (experiment for round 2, OFF) the TMA tile kernel is instantiated per colour space and takes the
-//                 transform's coefficients as compile-time constants (IMAD with an immediate operand) instead of
-//                 twelve registers loaded from the launch parameters - registers a wider tile visit can use
+//   SCOPE_IMMCOEF the TMA tile kernels that evaluate the transform are instantiated per colour space and take its
+//                 coefficients as compile-time constants (IMAD with an immediate operand) instead of twelve registers
+//                 loaded from the launch parameters: 9 registers fewer and no per-visit reload (measured +2 %,
+//                 profiles/r02/ab_round2.md; it is what lets 20 warps run the pipelined loop in 80 registers)
 #ifndef SCOPE_IMMCOEF
-#define SCOPE_IMMCOEF 0
+#define SCOPE_IMMCOEF 1
 #endif
 //   SCOPE_WIDE_FUSED (experiment for round 2, OFF) tile geometry per kernel family: the kernels that hold the
 //                 vectorscope (one CTA per SM, 120 registers through __maxnreg__) take tiles of twice the height,
@@ -119,14 +120,31 @@ constexpr int kStripPx = 32;          // columns per strip == lanes per warp
 #ifndef SCOPE_DEPHASE
 #define SCOPE_DEPHASE 0
 #endif
+//   SCOPE_FUSED_WARPS consumer warps of the kernels that hold the vectorscope bins and read ONE plane (one CTA per
+//                 SM; the fused headline pass is one of them).  The register file is per scheduler (16 K registers for
+//                 the warps w with w mod 4 == s): 17 warps (16 + producer) put 5 on one scheduler = at most 96
+//                 registers per thread, 21 put 6 = at most 80 - and the loop needs 80 with SCOPE_IMMCOEF.  Measured on
+//                 the mixed 4K batch (profiles/r02/ab_round2.md): 16 warps 33.9 %, 18: 33.8 %, 19: 34.7 %, 20: 36.1 %,
+//                 21: 35.0 %, 22: 35.8 %, 23: 37.1 % of the HBM peak (23 + the producer = 6 warps on every scheduler;
+//                 with a two-stage ring 23 warps fell to 31.5 %: the ring must hold three tiles).  The pass is bound
+//                 by per-warp latency, not by instruction count: 8 rows per visit (33 instead of 39 instructions per
+//                 pixel-warp, 15 warps, two stages) measured 32.1 %.
+#ifndef SCOPE_TMA_WARPS
+#define SCOPE_TMA_WARPS 16
+#define SCOPE_TMA_WARPS_DEFAULTED 1
+#endif
+#ifndef SCOPE_FUSED_WARPS
+#if defined(SCOPE_TMA_WARPS_DEFAULTED) && !defined(SCOPE_TILE_ROWS)
+#define SCOPE_FUSED_WARPS 23
+#else
+#define SCOPE_FUSED_WARPS SCOPE_TMA_WARPS // an A/B build that names a warp count or a tile height means it for every kernel
+#endif
+#endif
 #ifndef SCOPE_TILE_ROWS
 #define SCOPE_TILE_ROWS 64
 #endif
-#ifndef SCOPE_TMA_WARPS
-#define SCOPE_TMA_WARPS 16
-#endif
-constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile (SCOPE_WIDE_FUSED: twice that for some kernels, see SmemLayout)
-constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernel (kTileRows / kTmaWarps rows each)
+constexpr int kTileRows = SCOPE_TILE_ROWS; // rows per TMA tile of the 16-warp kernels (per kernel family: SmemLayout::kTileRows)
+constexpr int kTmaWarps = SCOPE_TMA_WARPS; // consumer warps of the TMA kernels that run two CTAs per SM or read two planes
 // SCOPE_GROUP_WARPS > 0 selects the row-group kernel (scope_strip_kernel_tmag) with that many
 // consumer warps for every TMA launch; 0 keeps the tile-synchronous kernel above
 #ifndef SCOPE_GROUP_WARPS
@@ -143,7 +161,8 @@ constexpr int kGroupRows = 4;                    // rows per group == rows one l
 constexpr int kSplitVsWarps = SCOPE_SPLIT_VS_WARPS;   // specialised kernel: warps doing transform + vectorscope
 constexpr int kSplitBinWarps = SCOPE_SPLIT_BIN_WARPS; // specialised kernel: warps doing the column bins
 constexpr int kBallotLanes = 8;            // SCOPE_BALLOT: lanes that must agree before a block takes the aggregating path
-constexpr int kRingBytes = 32768;          // shared memory the bins leave for the tile ring
+constexpr int kRingBytes = 35328;          // shared memory the bins leave for the tile ring: 227 KB - 128 KB (vectorscope) - 64 KB
+                                           // (column bins) - barriers and mailbox; 4 stages of 64-row tiles, 3 of 80- to 92-row tiles
 constexpr int kMaxStages = 8;              // upper bound of the ring depth (barrier storage)
 constexpr int kTileBytes = kStripPx * 4 * kTileRows; // 8 KB per plane per stage
 #ifndef SCOPE_MAX_CHUNK
@@ -156,6 +175,7 @@ constexpr int kMaxChunkItems = SCOPE_MAX_CHUNK; // upper bound of strips per dyn
 constexpr int kQueue = SCOPE_DEEP_RING ? 8 : 4;
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
+constexpr int kMaxWaveCopies = 15;    // extra destinations of the final waveform (scope_accumulate_band: <= 16 ranks)
 constexpr int kVsWords = 32768;       // 65536 vectorscope bins, two u16 per word
 constexpr int kWaveWords = 256 * 32;  // one plane: [level][lane]
 
@@ -182,7 +202,10 @@ struct StripParams {
 	uint32_t wave_mask;       // channels the waveform output wants
 	uint32_t x_offset;        // first output column (tile-sharded frames)
 	uint32_t out_width;       // row length of the waveform output in pixels
-	uint32_t partial;         // 1: add u16 pairs into wave_pairs instead of writing u8
+	uint32_t partial;         // 0: write the final u8 waveform; 1: ADD u16 pairs into wave_pairs (several tiles share
+	                          // the columns: caller-zeroed accumulators, global atomics); 2: STORE the u16 pairs (this
+	                          // launch is the only writer of its columns: no zero-fill, no atomics)
+	uint32_t n_wave_copies;   // final u8 waveform also goes to wave_copies[0 .. n): the other ranks' images (peer stores)
 	uint32_t tma_x0_rgb, tma_x0_yuv; // TMA kernels: pixel column of the plane's first pixel inside its tensor map
 	                                 // (the map starts at the plane pointer rounded down to 16 bytes)
 	uint32_t *chunk_counter;  // global work counter of this launch (zeroed by the host)
@@ -191,6 +214,7 @@ struct StripParams {
 	uint32_t *wave_pairs;     // partial: [2][256][out_width]: plane 0 = (B|U : lo16, G|Y : hi16), plane 1 = R|V
 	uint32_t *vscope_acc;     // [n][65536] u32, zeroed
 	unsigned long long hist_stride, wave_stride, vscope_stride; // elements between frames
+	uint8_t *wave_copies[kMaxWaveCopies]; // column-band sharding: every rank's image gets this rank's columns
 	Coef coef;
 };
 
@@ -505,8 +529,13 @@ struct SmemLayout {
 	static constexpr int kWave0Off = kVsOff + kVsBytes;
 	static constexpr int kWaveBytes = SRC != SRC_NONE ? 2 * kWaveWords * 4 : 0;
 	static constexpr int kStageOff = kWave0Off + kWaveBytes;
-	// tile height of this kernel family (the two-plane surface-mode ring has no room for taller tiles)
-	static constexpr int kTileRows = (SCOPE_WIDE_FUSED && VSCOPE && kPlanes == 1) ? 2 * scope::kTileRows : scope::kTileRows;
+	// consumer warps and tile height of this kernel family: the one-plane kernels with the vectorscope (one CTA per
+	// SM) run SCOPE_FUSED_WARPS warps; the two-CTA kernels and the two-plane surface-mode ring (no room for taller
+	// tiles) keep kTmaWarps.  Every warp takes kRowsPerWarp rows of a tile.
+	static constexpr bool kOnePlaneVs = VSCOPE && kPlanes == 1;
+	static constexpr int kWarps = (USE_TMA && kOnePlaneVs && !SCOPE_WIDE_FUSED) ? SCOPE_FUSED_WARPS : kTmaWarps;
+	static constexpr int kRowsPerWarp = (scope::kTileRows / kTmaWarps) * ((SCOPE_WIDE_FUSED && kOnePlaneVs) ? 2 : 1);
+	static constexpr int kTileRows = kWarps * kRowsPerWarp;
 	static constexpr int kTileBytes = kStripPx * 4 * kTileRows;
 	static constexpr int kStageBytes = USE_TMA ? kPlanes * kTileBytes : 0;
 	// two planes per stage (surface mode) leave room for a 2-deep ring only
@@ -852,7 +881,8 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 	workers_bar<NW>();
 	uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
 	const uint32_t xo = P.x_offset + x;
-	if (SCOPE_FAST_EMIT && NW >= 8 && !P.partial && P.wave_mask == 7u && (P.hist_mask == 7u || P.hist_mask == 0u)) {
+	if (SCOPE_FAST_EMIT && NW >= 8 && !P.partial && !P.n_wave_copies && P.wave_mask == 7u &&
+	    (P.hist_mask == 7u || P.hist_mask == 0u)) {
 		// The common case (all three channels to the waveform, all or none to the histogram),
 		// without per-level tests of launch-uniform flags.  Levels whose 32 columns are all empty
 		// (most levels, for picture content) only get their zero row written.  The warp's column
@@ -924,14 +954,24 @@ __device__ __forceinline__ void emit_strip(const StripParams &P, uint32_t *wave0
 			const uint32_t mg = (P.wave_mask & 2u) ? cg : 0u;
 			const uint32_t mr = (P.wave_mask & 4u) ? cr : 0u;
 			const size_t o = (size_t)(255 - v) * P.out_width + xo;
-			if (P.partial) {
+			if (P.partial == 2u) {
+				// the only writer of these columns (a row band accumulated in one launch): plain stores
+				P.wave_pairs[o] = mb | (mg << 16);
+				if (P.wave_mask & 4u) // plane 1 only exists for the R|V channel
+					P.wave_pairs[(size_t)256 * P.out_width + o] = mr;
+			} else if (P.partial) {
 				if (mb | mg)
 					atomicAdd(P.wave_pairs + o, mb | (mg << 16));
 				if (mr)
 					atomicAdd(P.wave_pairs + (size_t)256 * P.out_width + o, mr);
 			} else {
+				const uint32_t word = min(mb, 255u) | (min(mg, 255u) << 8) | (min(mr, 255u) << 16);
 				uint32_t *dst = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride);
-				dst[o] = min(mb, 255u) | (min(mg, 255u) << 8) | (min(mr, 255u) << 16);
+				dst[o] = word;
+				// column bands over several GPUs: the same columns of every other rank's image
+				// (NVLink peer stores, 128 bytes per warp and row: the all-gather happens here)
+				for (uint32_t c = 0; c < P.n_wave_copies; c++)
+					reinterpret_cast<uint32_t *>(P.wave_copies[c])[o] = word;
 			}
 		}
 	}
@@ -1514,7 +1554,7 @@ constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
 #if defined(SCOPE_MAXNREG) && !defined(SCOPE_EMULATE)
 #define SCOPE_TMA_BOUNDS __maxnreg__((kTmaMinCtas<SRC, VSCOPE, SURFACE> == 1 ? SCOPE_MAXNREG : 56))
 #else
-#define SCOPE_TMA_BOUNDS __launch_bounds__(kTmaWarps * 32 + 32, kTmaMinCtas<SRC, VSCOPE, SURFACE>)
+#define SCOPE_TMA_BOUNDS __launch_bounds__((SmemLayout<SRC, VSCOPE, SURFACE, true>::kWarps * 32 + 32), kTmaMinCtas<SRC, VSCOPE, SURFACE>)
 #endif
 template <int SRC, bool VSCOPE, bool SURFACE, int CS = 0>
 __global__ void SCOPE_TMA_BOUNDS
@@ -1522,7 +1562,7 @@ __global__ void SCOPE_TMA_BOUNDS
 			       const __grid_constant__ CUtensorMap map_yuv)
 {
 	using L = SmemLayout<SRC, VSCOPE, SURFACE, true>;
-	constexpr int NW = kTmaWarps, RPW = L::kTileRows / NW;
+	constexpr int NW = L::kWarps, RPW = L::kRowsPerWarp;
 	SCOPE_DYNAMIC_SMEM(smem);
 	volatile uint32_t *chunk_q = reinterpret_cast<volatile uint32_t *>(smem + L::kQueueOff);
 	const uint32_t smem_base = smem_u32(smem);
@@ -1541,8 +1581,11 @@ __global__ void SCOPE_TMA_BOUNDS
 										  bar_empty, warp * RPW, warp, lane, tid);
 }
 
-// the kernels that were measured and not adopted: row-group consumer, warp-specialised kernel
+// the kernels that were measured and not adopted (row-group consumer, warp-specialised kernel): A/B builds
+// (-DSCOPE_EXPERIMENT) and the CPU emulator only; the shipped library does not carry them
+#if defined(SCOPE_EXPERIMENT) || defined(SCOPE_EMULATE)
 #include "scope_kernels_experiments.cuh"
+#endif
 
 // ---------------------------------------------------------------------------
 // strip kernel, plain-load fallback for planes TMA cannot describe (base or pitch not a
@@ -1694,12 +1737,14 @@ __global__ void __launch_bounds__(256) wave_display_kernel(const uint8_t *wave, 
 }
 
 // partial (tile-sharded) waveform: summed u16 pairs (two planes) -> saturated u8 BGRX
-__global__ void __launch_bounds__(256) wave_pairs_finalize_kernel(const uint32_t *pairs, uint8_t *wave, size_t n_px)
+// (plane 1 = the R|V channel is only read when the waveform has that channel: otherwise it need not hold valid data)
+__global__ void __launch_bounds__(256) wave_pairs_finalize_kernel(const uint32_t *pairs, uint8_t *wave, size_t n_px,
+								  int plane1)
 {
 	const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
 	if (i >= n_px)
 		return;
-	const uint32_t w0 = pairs[i], w1 = pairs[n_px + i];
+	const uint32_t w0 = pairs[i], w1 = plane1 ? pairs[n_px + i] : 0u;
 	reinterpret_cast<uint32_t *>(wave)[i] =
 		min(w0 & 0xFFFFu, 255u) | (min(w0 >> 16, 255u) << 8) | (min(w1 & 0xFFFFu, 255u) << 16);
 }

@@ -253,6 +253,48 @@ class ScopeEngine:
         self.ctx.check(self.lib.scope_accumulate_partial(self.ctx.handle, C.byref(p), C.byref(s), x_offset,
                                                          full_width, C.byref(pd), C.c_void_p(stream)))
 
+    def accumulate_band(self, tile, partial=None, *, x_offset: int, full_width: int, wave_outs=None,
+                        exclusive: bool = False, yuv_tile=None, settings: Optional[ScopeSettings] = None,
+                        width: Optional[int] = None, stream: Optional[int] = None):
+        """``scope_accumulate_band``: one band of a tile-sharded frame.
+
+        ``exclusive=True``: this call is the only writer of its columns of ``partial["wave_pairs"]`` (a row band
+        accumulated in one call): pairs are stored, not added - no zero-fill, no atomics.
+        ``wave_outs``: list of waveform images (CUDA tensors shaped like ``alloc_device_out(1, ...)["wave"]`` or plain
+        device addresses, e.g. peer mappings) that receive this band's FINAL columns - only for bands that span the
+        full height (column bands); the waveform then needs no partial and no reduce."""
+        import torch
+
+        st = settings or ScopeSettings()
+        ref = tile if tile is not None else yuv_tile
+        if ref.dim() == 3 and ref.shape[-1] == 4 and width is None:
+            h, w, _ = ref.shape
+            assert ref.stride(2) == 1 and ref.stride(1) == 4
+            width = w
+        else:
+            h = ref.shape[0]
+            assert width is not None
+        s = Surface()
+        s.rgb_data = tile.data_ptr() if tile is not None else None
+        s.yuv_data = yuv_tile.data_ptr() if yuv_tile is not None else None
+        s.linesize, s.width, s.height, s.colorspace = ref.stride(0), width, h, st.colorspace
+        pd = None
+        if partial is not None:
+            pd = PartialDevice()
+            pd.hist_counts = partial["hist"].data_ptr() if "hist" in partial else None
+            pd.wave_pairs = partial["wave_pairs"].data_ptr() if "wave_pairs" in partial else None
+            pd.vscope_counts = partial["vscope"].data_ptr() if "vscope" in partial else None
+        outs, n_outs = None, 0
+        if wave_outs:
+            n_outs = len(wave_outs)
+            outs = (C.c_void_p * n_outs)(*[(o.data_ptr() if hasattr(o, "data_ptr") else int(o)) for o in wave_outs])
+        if stream is None:
+            stream = torch.cuda.current_stream(ref.device).cuda_stream
+        p = st.to_c()
+        self.ctx.check(self.lib.scope_accumulate_band(self.ctx.handle, C.byref(p), C.byref(s), x_offset, full_width,
+                                                      C.byref(pd) if pd is not None else None, outs, n_outs,
+                                                      _ffi.BAND_EXCLUSIVE if exclusive else 0, C.c_void_p(stream)))
+
     def finalize_partial(self, partial, *, full_width: int, full_height: int,
                          settings: Optional[ScopeSettings] = None, stream: Optional[int] = None):
         import torch

@@ -78,53 +78,86 @@ def gather_results(out: Dict[str, "torch.Tensor"], dst: int = 0, group=None) -> 
 
 
 class TiledFrame:
-    """One frame split across ranks.  Each rank calls `accumulate(band_tensor)` with ITS band
-    (device tensor) and then `reduce_and_finalize()`; every rank ends with the full result."""
+    """One frame split across ranks, cross-rank step by NCCL.  Each rank calls `accumulate(band_tensor)` with ITS
+    band (device tensor) and then `reduce_and_finalize()`; every rank ends with the full result.
+
+    rows: every rank holds partial sums for all columns -> all-reduce (sum) of the partials, then saturate.
+    cols: the waveform columns of a rank are FINAL (its band spans the full height): they are written as u8 and
+          all-gathered (1/4 of the bytes of the u16-pair all-reduce, and no clamp pass); histogram and vectorscope
+          partials (260 KB) are still all-reduced.  Needs bands of equal width (else the waveform falls back to the
+          all-reduce of the pairs, which merges disjoint columns exactly as well)."""
 
     def __init__(self, engine, full_width: int, full_height: int, settings, mode: str = "rows", group=None):
         import torch.distributed as dist
 
         assert mode in ("rows", "cols")
+        assert full_height <= 65535, "u16 halves of the partial waveform: a frame has at most 65535 rows"
         self.engine, self.settings, self.mode, self.group = engine, settings, mode, group
         self.width, self.height = full_width, full_height
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bands = row_bands(full_height, self.world) if mode == "rows" else col_bands(full_width, self.world)
         self.partial = engine.alloc_partial(full_width)
+        from ._ffi import SCOPE_WAVE
+        widths = {b - a for a, b in self.bands}
+        self.gather_wave = (mode == "cols" and bool(settings.scopes & SCOPE_WAVE) and len(widths) == 1
+                            and settings.wave_intensity == 0)
+        if self.gather_wave:
+            import torch
+            bw = self.bands[0][1] - self.bands[0][0]
+            dev = self.partial["hist"].device
+            self._band_img = torch.empty((256, bw, 4), dtype=torch.uint8, device=dev)
+            self._gathered = torch.empty((self.world, 256, bw, 4), dtype=torch.uint8, device=dev)
 
     @property
     def my_band(self) -> Tuple[int, int]:
         return self.bands[self.rank]
 
-    def reset(self):
-        for t in self.partial.values():
-            t.zero_()
-
-    def accumulate(self, band, width: Optional[int] = None):
-        """band: this rank's rows (rows mode: (h_band, W, 4)) or columns (cols mode: a
-        (H, linesize) byte view starting at column x0, with `width` = x1 - x0)."""
-        a, b = self.my_band
-        if self.mode == "rows":
-            self.engine.accumulate_partial(band, self.partial, x_offset=0, full_width=self.width,
-                                           settings=self.settings, width=width)
-        else:
-            self.engine.accumulate_partial(band, self.partial, x_offset=a, full_width=self.width,
-                                           settings=self.settings, width=(b - a) if width is None else width)
-
-    def _reduce_keys(self):
-        from ._ffi import SCOPE_HIST, SCOPE_VSCOPE, SCOPE_WAVE
+    def _other_keys(self):
+        from ._ffi import SCOPE_HIST, SCOPE_VSCOPE
 
         keys = []
         if self.settings.scopes & SCOPE_HIST:
             keys.append("hist")
-        if self.settings.scopes & SCOPE_WAVE:
-            keys.append("wave_pairs")       # cols mode: disjoint columns, the sum just merges them
         if self.settings.scopes & SCOPE_VSCOPE:
             keys.append("vscope")
         return keys
 
+    def reset(self):
+        """zero what the next accumulate() ADDS to.  A band accumulated in one call stores its waveform pairs
+        (SCOPE_BAND_EXCLUSIVE) or writes final u8 columns, so the 2 x 256 x W pairs need no zero-fill."""
+        for k in self._other_keys():
+            self.partial[k].zero_()
+
+    def accumulate(self, band, width: Optional[int] = None):
+        """band: this rank's rows (rows mode: (h_band, W, 4)) or columns (cols mode: a
+        (H, linesize) byte view starting at column x0, with `width` = x1 - x0).  ONE call per frame and rank."""
+        a, b = self.my_band
+        others = {k: self.partial[k] for k in self._other_keys()}
+        if self.mode == "rows":
+            part = dict(others, wave_pairs=self.partial["wave_pairs"])
+            self.engine.accumulate_band(band, part, x_offset=0, full_width=self.width, exclusive=True,
+                                        settings=self.settings, width=width)
+        elif self.gather_wave:
+            # final u8 columns of this band into a band-wide image (row length = band width)
+            self.engine.accumulate_band(band, others or None, x_offset=0, full_width=b - a,
+                                        wave_outs=[self._band_img], settings=self.settings,
+                                        width=(b - a) if width is None else width)
+        else:
+            part = dict(others, wave_pairs=self.partial["wave_pairs"])
+            self.engine.accumulate_band(band, part, x_offset=a, full_width=self.width, exclusive=True,
+                                        settings=self.settings, width=(b - a) if width is None else width)
+
+    def _reduce_keys(self):
+        from ._ffi import SCOPE_WAVE
+
+        keys = self._other_keys()
+        if (self.settings.scopes & SCOPE_WAVE) and not self.gather_wave:
+            keys.append("wave_pairs")
+        return keys
+
     def start_reduce(self):
-        """Enqueue the all-reduce of this frame's partials without waiting for it, so the caller
+        """Enqueue the collectives of this frame without waiting for them, so the caller
         can accumulate the next frame (into another TiledFrame) while NCCL runs."""
         import torch.distributed as dist
 
@@ -133,15 +166,35 @@ class TiledFrame:
             planes = 2 if (self.settings.wave_components & 0x44) else 1
             for k in self._reduce_keys():
                 t = self.partial[k][:planes] if k == "wave_pairs" else self.partial[k]
+                if k == "wave_pairs" and self.mode == "cols":
+                    # stored (not added) pairs: columns of other ranks hold stale data -> zero them first
+                    a, b = self.my_band
+                    t[:, :, :a].zero_()
+                    t[:, :, b:].zero_()
                 self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self.gather_wave:
+                self._works.append(dist.all_gather_into_tensor(self._gathered, self._band_img, group=self.group,
+                                                               async_op=True))
+        elif self.gather_wave:
+            self._gathered[0].copy_(self._band_img)
 
     def finish(self):
         """Wait for start_reduce() (stream-side) and saturate into the reference layouts."""
         for w in getattr(self, "_works", []):
             w.wait()
         self._works = []
-        return self.engine.finalize_partial(self.partial, full_width=self.width, full_height=self.height,
-                                            settings=self.settings)
+        if not self.gather_wave:
+            return self.engine.finalize_partial(self.partial, full_width=self.width, full_height=self.height,
+                                                settings=self.settings)
+        from dataclasses import replace
+        from ._ffi import SCOPE_WAVE
+
+        st = replace(self.settings, scopes=self.settings.scopes & ~SCOPE_WAVE)
+        out = (self.engine.finalize_partial(self.partial, full_width=self.width, full_height=self.height, settings=st)
+               if st.scopes else {})
+        # [rank][256][bw][4] -> [256][rank * bw][4]: the bands side by side
+        out["wave"] = self._gathered.permute(1, 0, 2, 3).reshape(1, 256, self.width, 4)
+        return out
 
     def reduce_and_finalize(self):
         self.start_reduce()
@@ -170,11 +223,16 @@ class PeerTiledFrame(TiledFrame):
         import torch.distributed as dist
 
         assert mode in ("rows", "cols")
+        assert full_height <= 65535, "u16 halves of the partial waveform: a frame has at most 65535 rows"
         self.engine, self.settings, self.mode, self.group = engine, settings, mode, group
         self.width, self.height = full_width, full_height
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bands = row_bands(full_height, self.world) if mode == "rows" else col_bands(full_width, self.world)
+        self.gather_wave = False
+        from ._ffi import SCOPE_WAVE as _W
+        # column bands: the strip kernel stores its final waveform columns straight into every rank's image
+        self.direct_wave = mode == "cols" and bool(settings.scopes & _W) and settings.wave_intensity == 0
         self.two_shot = (self.world > 2) if two_shot is None else (bool(two_shot) and self.world > 1)
         self.nvls = bool(nvls) and self.world > 1
         self._mc_base = 0
@@ -229,9 +287,26 @@ class PeerTiledFrame(TiledFrame):
         return {key: self._bases[rank] + 4 * self._off[sec] for key, sec in names if sec in self._off}
 
     def reset(self):
-        """zero the partials for the next frame (after reduce_and_finalize's closing barrier nobody reads them);
-        they are the first three sections of the allocation: one memset"""
-        self._buf[:self._off["out_wave"]].zero_()
+        """zero what the next accumulate() ADDS to: histogram and vectorscope partials (the first two sections of the
+        allocation, one memset of 260 KB) when those scopes are on.  The waveform pairs are stored, not added
+        (SCOPE_BAND_EXCLUSIVE), or not used at all (column bands): no zero-fill."""
+        if self._other_keys():
+            self._buf[:self._off["wave_pairs"]].zero_()
+
+    def accumulate(self, band, width: Optional[int] = None):
+        a, b = self.my_band
+        others = {k: self.partial[k] for k in self._other_keys()}
+        if self.mode == "rows" or not self.direct_wave:
+            part = dict(others, wave_pairs=self.partial["wave_pairs"])
+            self.engine.accumulate_band(band, part, x_offset=0 if self.mode == "rows" else a, full_width=self.width,
+                                        exclusive=True, settings=self.settings,
+                                        width=width if self.mode == "rows" else ((b - a) if width is None else width))
+            return
+        # column bands: my columns of EVERY rank's image, mine first (local), the others over NVLink
+        off = 4 * self._off["out_wave"]
+        outs = [self._bases[self.rank] + off] + [self._bases[r] + off for r in range(self.world) if r != self.rank]
+        self.engine.accumulate_band(band, others or None, x_offset=a, full_width=self.width, wave_outs=outs,
+                                    settings=self.settings, width=(b - a) if width is None else width)
 
     def finish(self):
         """results of the last start_reduce() (everything is stream-ordered; nothing to wait for on the host)"""
@@ -247,21 +322,34 @@ class PeerTiledFrame(TiledFrame):
         out_names = [("wave", "out_wave"), ("vscope", "out_vscope"), ("wave_display", "out_wave_display"),
                      ("vscope_display", "out_vscope_display")]
         if self._hdl is not None:
-            self._hdl.barrier(channel=0)         # every rank's accumulate_partial is complete and visible
+            self._hdl.barrier(channel=0)         # every rank's accumulate is complete and visible
+        st = self.settings
+        if self.direct_wave:
+            # the waveform is already in every rank's image (the barrier above completes it); what is left is the
+            # 260 KB of histogram / vectorscope partials, if those scopes are on
+            from dataclasses import replace
+            from ._ffi import SCOPE_WAVE
+            st = replace(st, scopes=st.scopes & ~SCOPE_WAVE)
+            if not st.scopes:
+                return
+            part_names = [pn for pn in part_names if pn[0] != "wave_pairs"]
+            out_names = [on for on in out_names if not on[0].startswith("wave")]
         partials = [self._addresses(r, part_names) for r in range(self.world)]
         mine = dict(self._addresses(self.rank, out_names))
         for k in ("hist", "hist_max"):
             if k in self.out:
                 mine[k] = self.out[k]
-        mine = {k: v for k, v in mine.items() if k in self.out}
+        mine = {k: v for k, v in mine.items() if k in self.out and not (self.direct_wave and k.startswith("wave"))}
         if self.nvls:
             # the switch sums (multimem.ld_reduce) and, two-shot, replicates the slice into every rank's images
             mc = self._mc_base
             mc_partial = {key: mc + 4 * self._off[sec] for key, sec in part_names}
+            for key in ("hist", "wave_pairs", "vscope"):
+                mc_partial.setdefault(key, None)
             mc_images = ({key: mc + 4 * self._off[sec] for key, sec in out_names if sec in self._off and key in self.out}
                          if self.two_shot else None)
             self.engine.finalize_multicast(mc_partial, mine, mc_images, full_width=self.width, full_height=self.height,
-                                           settings=self.settings, slice_index=self.rank if self.two_shot else 0,
+                                           settings=st, slice_index=self.rank if self.two_shot else 0,
                                            slice_count=self.world if self.two_shot else 1)
             self._hdl.barrier(channel=1)
             return
@@ -270,7 +358,7 @@ class PeerTiledFrame(TiledFrame):
             outs += [{k: v for k, v in self._addresses(r, out_names).items() if k in self.out}
                      for r in range(self.world) if r != self.rank]
         self.engine.finalize_peers(partials, outs, full_width=self.width, full_height=self.height,
-                                   settings=self.settings, slice_index=self.rank if self.two_shot else 0,
+                                   settings=st, slice_index=self.rank if self.two_shot else 0,
                                    slice_count=self.world if self.two_shot else 1)
         if self._hdl is not None:
             self._hdl.barrier(channel=1)         # peers are done reading my partials / writing my images

@@ -19,6 +19,9 @@ def test_reference_arm_json_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms describe the workload with the same `config` object (same keys, same values)
+    sys.path.insert(0, ROOT)
+    assert set(line["config"]) == {"workload", "frames_per_gpu", "global_batch", "width", "height", "parallelism", "l2"}
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -34,18 +34,26 @@ def _worker(rank, world, port, q):
     w, h = 1000, 700
     full = frames_torch.mixed_batch(1, w, h, dev, first_index=3, content="natural")[0]   # same seed on every rank
     whole = eng.accumulate_device(full[None])
-    for mode in ("rows", "cols"):
-        tiled = pkg.sharding.TiledFrame(eng, w, h, pkg.ScopeSettings(), mode=mode)
+    w2 = 1024   # equal column bands (32 strips over 2 ranks): the all-gather form of the NCCL column mode
+    full2 = frames_torch.mixed_batch(1, w2, h, dev, first_index=5, content="natural")[0]
+    whole2 = eng.accumulate_device(full2[None])
+    for mode, fw, ff, wh in (("rows", w, full, whole), ("cols", w, full, whole), ("cols", w2, full2, whole2)):
+        tiled = pkg.sharding.TiledFrame(eng, fw, h, pkg.ScopeSettings(), mode=mode)
         a, b = tiled.my_band
-        if mode == "rows":
-            tiled.accumulate(full[a:b])
-        else:
-            band = torch.as_strided(full.reshape(-1)[a * 4:], (h, (w - a) * 4), (w * 4, 1))
-            tiled.accumulate(band, width=b - a)
-        out = tiled.reduce_and_finalize()
-        torch.cuda.synchronize()
-        for k in ("hist", "wave", "vscope"):
-            ok = ok and bool(torch.equal(out[k][0], whole[k][0]))
+        for rep in range(2):
+            tiled.reset()
+            if mode == "rows":
+                tiled.accumulate(ff[a:b])
+            else:
+                band = torch.as_strided(ff.reshape(-1)[a * 4:], (h, (fw - a) * 4), (fw * 4, 1))
+                tiled.accumulate(band, width=b - a)
+            out = tiled.reduce_and_finalize()
+            torch.cuda.synchronize()
+            for k in ("hist", "wave", "vscope"):
+                same = bool(torch.equal(out[k][0], wh[k][0]))
+                if not same:
+                    print(f"rank {rank}: TiledFrame {mode} w={fw} gather={tiled.gather_wave}: {k} differs", flush=True)
+                ok = ok and same
     # frame sharding + optional gather
     n = 6
     batch = frames_torch.mixed_batch(n, 640, 360, dev)
@@ -83,18 +91,47 @@ def _peer_worker(rank, world, port, q):
     forms = [(False, False), (True, False)]
     if probe.multicast_ptr:                       # the NVLS forms only where the switch offers multicast
         forms += [(False, True), (True, True)]
-    for two_shot, nvls in forms:
-        tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st, mode="rows", two_shot=two_shot, nvls=nvls)
+    def band_of(full, tiled, mode):
         a, b = tiled.my_band
+        if mode == "rows":
+            return full[a:b], None
+        return torch.as_strided(full.reshape(-1)[a * 4:], (h, (w - a) * 4), (w * 4, 1)), b - a
+
+    for mode in ("rows", "cols"):
+        for two_shot, nvls in forms:
+            tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st, mode=mode, two_shot=two_shot, nvls=nvls)
+            for index in (3, 7):
+                full = frames_torch.mixed_batch(1, w, h, dev, first_index=index, content="natural")[0]
+                whole = eng.accumulate_device(full[None], settings=st)
+                tiled.reset()
+                band, bw = band_of(full, tiled, mode)
+                tiled.accumulate(band, width=bw)
+                out = tiled.reduce_and_finalize()
+                torch.cuda.synchronize()
+                dist.barrier()
+                for k in ("hist", "hist_max", "wave", "vscope", "vscope_display"):
+                    same = bool(torch.equal(out[k][0], whole[k][0]))
+                    if not same:
+                        print(f"rank {rank}: PeerTiledFrame {mode} two_shot={two_shot} nvls={nvls} frame {index}: {k} differs", flush=True)
+                    ok = ok and same
+    # BASELINE config 4 in small: luma waveform only (components 0x20); column bands = the strip kernel's own peer
+    # stores + one barrier, row bands = exclusive pairs + the fused reduce
+    st4 = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=0x20)
+    for mode in ("rows", "cols"):
+        tiled = pkg.sharding.PeerTiledFrame(eng, w, h, st4, mode=mode)
         for index in (3, 7):
             full = frames_torch.mixed_batch(1, w, h, dev, first_index=index, content="natural")[0]
-            whole = eng.accumulate_device(full[None], settings=st)
+            whole = eng.accumulate_device(full[None], settings=st4)
             tiled.reset()
-            tiled.accumulate(full[a:b])
+            band, bw = band_of(full, tiled, mode)
+            tiled.accumulate(band, width=bw)
             out = tiled.reduce_and_finalize()
             torch.cuda.synchronize()
-            for k in ("hist", "hist_max", "wave", "vscope", "vscope_display"):
-                ok = ok and bool(torch.equal(out[k][0], whole[k][0]))
+            dist.barrier()
+            same = bool(torch.equal(out["wave"][0], whole["wave"][0]))
+            if not same:
+                print(f"rank {rank}: config-4 {mode} frame {index}: waveform differs", flush=True)
+            ok = ok and same
     q.put((rank, ok))
     dist.destroy_process_group()
     eng.close()

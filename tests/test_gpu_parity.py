@@ -254,20 +254,3 @@ def test_surface_mode_matches_reference_golden(engine, pkg, case):
                                       g[f"{case}/hist/{comp:02x}/{key}"].view(np.uint32)), (case, hex(comp), key)
         assert np.array_equal(res["wave"], g[f"{case}/wave/{comp:02x}"]), (case, hex(comp))
         assert np.array_equal(res["vscope"], g[f"{case}/vscope"]), case
-
-
-@pytest.mark.gpu
-def test_row_group_kernel_parity(engine, oracle, pkg, monkeypatch):
-    """The row-group kernel (SCOPE_KERNEL=group) is not the default but stays
-    selectable: same bytes as the oracle, including heights that are not a multiple of the tile or
-    the group height and strips narrower than 32 columns."""
-    monkeypatch.setenv("SCOPE_KERNEL", "group")
-    fr = pkg.frames
-    for f in (fr.random(640, 360, seed=3), fr.natural(333, 131, seed=1), fr.solid(96, 70), fr.alpha_stripes(200, 66),
-              fr.ramp(64, 3)):
-        for cs in (1, 2):
-            res = engine.accumulate_host(f, settings=pkg.ScopeSettings(colorspace=cs))
-            yuv = oracle.rgb_to_yuv(f, cs)
-            assert np.array_equal(res["hist"], oracle.histogram_counts(0x07, f, yuv))
-            assert np.array_equal(res["wave"], oracle.waveform(0x07, f, yuv))
-            assert np.array_equal(res["vscope"], oracle.vectorscope(yuv))

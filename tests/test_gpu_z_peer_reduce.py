@@ -141,3 +141,43 @@ def test_peer_tiled_frame_single_rank(engine, oracle, pkg):
         torch.cuda.synchronize()
         _check(out, oracle, f, yuv, st)
         assert np.array_equal(out["hist"][0].cpu().numpy().view(np.uint32), oracle.histogram_counts(7, f, yuv).ravel())
+
+
+def test_accumulate_band_exclusive_and_direct_columns(engine, oracle, pkg):
+    """scope_accumulate_band: (a) SCOPE_BAND_EXCLUSIVE - a band's waveform pairs are STORED into accumulators that
+    hold garbage (no zero-fill), row bands then summed by scope_finalize_peers; (b) column bands spanning the full
+    height write their FINAL waveform columns into several images at once (the peers' images on a multi-GPU box,
+    two local allocations here) while histogram and vectorscope go through partials."""
+    import torch
+    f = _frame(pkg)
+    d = torch.from_numpy(f).cuda()
+    yuv = oracle.rgb_to_yuv(f, 2)
+    st = pkg.ScopeSettings()
+    # (a) row bands, each into its own garbage-filled partial
+    parts = []
+    for y0, y1 in BANDS:
+        part = engine.alloc_partial(W)
+        part["wave_pairs"].fill_(0x5A5A5A5A)
+        engine.accumulate_band(d[y0:y1], part, x_offset=0, full_width=W, exclusive=True, settings=st)
+        parts.append(part)
+    out = engine.alloc_device_out(1, W, st)
+    engine.finalize_peers(parts, [out], full_width=W, full_height=H, settings=st)
+    torch.cuda.synchronize()
+    _check(out, oracle, f, yuv, st)
+    assert np.array_equal(out["hist"][0].cpu().numpy().view(np.uint32), oracle.histogram_counts(7, f, yuv).ravel())
+    # (b) column bands -> two images at once; luma-only (config 4's components) and RGB
+    for comp in (0x20, 0x07):
+        stc = pkg.ScopeSettings(wave_components=comp)
+        imgs = [torch.full((1, 256, W, 4), 0x6E, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        part = engine.alloc_partial(W)
+        for x0, x1 in [(0, 64), (64, 96), (96, W)]:
+            tile = torch.as_strided(d.reshape(-1)[x0 * 4:], (H, (W - x0) * 4), (W * 4, 1))
+            engine.accumulate_band(tile, {"hist": part["hist"], "vscope": part["vscope"]}, x_offset=x0, full_width=W,
+                                   wave_outs=imgs, settings=stc, width=x1 - x0)
+        torch.cuda.synchronize()
+        want = oracle.waveform(comp, f, yuv)
+        for im in imgs:
+            assert np.array_equal(im[0].cpu().numpy(), want), hex(comp)
+        assert np.array_equal(part["hist"].cpu().numpy().view(np.uint32), oracle.histogram_counts(7, f, yuv).ravel())
+        assert np.array_equal(np.minimum(part["vscope"].cpu().numpy().view(np.uint32), 255).astype(np.uint8).reshape(256, 256),
+                              oracle.vectorscope(yuv))

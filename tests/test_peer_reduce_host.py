@@ -187,8 +187,8 @@ def test_peer_tiled_frame_host_logic(host_lib, pkg, oracle, two_shot):
         for t, (hist, pairs, vs) in zip(ranks, parts):
             if frame:
                 assert all(bool(v.any()) for v in t.partial.values())
-            t.reset()
-            assert not any(bool(v.any()) for v in t.partial.values())
+            t.reset()     # zeroes what accumulate ADDS to; the waveform pairs are stored whole (SCOPE_BAND_EXCLUSIVE)
+            assert not bool(t.partial["hist"].any()) and not bool(t.partial["vscope"].any())
             t.partial["hist"].copy_(torch.from_numpy(hist))
             t.partial["wave_pairs"].copy_(torch.from_numpy(pairs))
             t.partial["vscope"].copy_(torch.from_numpy(vs))

@@ -18,7 +18,7 @@ ORDER="dephase wide_dephase wide_straight_dephase wide wide_straight w16n8_immco
 PT="timeout -s KILL 300 python -m pytest -x -q -m gpu tests"
 PV="timeout -s KILL 120 python -m pytest -x -q -m gpu tests/test_gpu_parity.py tests/test_gpu_properties.py"
 SHORT="fused_all_scopes_host or device_batch or saturation_solid or batch_order or tall_and_wide or tiles_add_up"
-B="timeout -s KILL 100 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
+B="timeout -s KILL 100 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-config4"
 $PT > $O/pytest.full 2>&1; echo "exit $?" >> $O/pytest.full; tail -6 $O/pytest.full > $O/pytest.log
 $B > $O/new_mixed.json 2>$O/new_mixed.err
 PASSED=""

@@ -97,6 +97,15 @@ void thread_entry()
 }
 
 template <int SRC, bool VS, bool SURF> int tile_rows_total() { return SmemLayout<SRC, VS, SURF, true>::kTileRows; }
+template <int SRC, bool VS, bool SURF> int tma_warps_total() { return SmemLayout<SRC, VS, SURF, true>::kWarps; }
+template <bool SURF> int tma_warps_for(int src, bool vs)
+{
+	if (src == SRC_NONE)
+		return tma_warps_total<SRC_NONE, true, SURF>();
+	if (src == SRC_RGB)
+		return vs ? tma_warps_total<SRC_RGB, true, SURF>() : tma_warps_total<SRC_RGB, false, SURF>();
+	return vs ? tma_warps_total<SRC_YUV, true, SURF>() : tma_warps_total<SRC_YUV, false, SURF>();
+}
 template <bool SURF> int tile_rows_for(int src, bool vs)
 {
 	if (src == SRC_NONE)
@@ -194,7 +203,8 @@ extern "C" int emul_run(EmulRequest *rq)
 		uint32_t ch = P.items / (grid * 6u);
 		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
 		P.chunk_counter = &chunk_counter;
-		threads = (rq->kernel == 2 ? kGroupWarps : kTmaWarps) * 32 + 32;
+		threads = (rq->kernel == 2 ? kGroupWarps
+					   : (l.surf ? tma_warps_for<true>(l.src, l.vs) : tma_warps_for<false>(l.src, l.vs))) * 32 + 32;
 	}
 	const int smem = l.surf ? smem_for<true>(l.src, l.vs, rq->kernel) : smem_for<false>(l.src, l.vs, rq->kernel);
 	if (smem > (int)emul::kSmemBytes) {
@@ -294,7 +304,7 @@ extern "C" int emul_run(EmulRequest *rq)
 
 extern "C" const char *emul_build_flags()
 {
-	static std::string s = std::string("warps=") + std::to_string(kTmaWarps) + " tile_rows=" + std::to_string(kTileRows) +
+	static std::string s = std::string("warps=") + std::to_string(kTmaWarps) + " fused_warps=" + std::to_string(SCOPE_FUSED_WARPS) + " tile_rows=" + std::to_string(kTileRows) +
 			       " straight=" + std::to_string(SCOPE_STRAIGHT) + " rawflat=" + std::to_string(SCOPE_RAWFLAT) +
 			       " wide_fused=" + std::to_string(SCOPE_WIDE_FUSED) + " immcoef=" + std::to_string(SCOPE_IMMCOEF) + " ballot=" + std::to_string(SCOPE_BALLOT) + " deep_ring=" + std::to_string(SCOPE_DEEP_RING) + " pipeline=" + std::to_string(SCOPE_PIPELINE) +
 			       " faddr=" + std::to_string(SCOPE_FADDR) + " ldsm=" + std::to_string(SCOPE_LDSM) +
