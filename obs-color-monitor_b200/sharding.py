@@ -123,11 +123,15 @@ class TiledFrame:
             keys.append("vscope")
         return keys
 
-    def reset(self):
+    def reset(self, additive: bool = False):
         """zero what the next accumulate() ADDS to.  A band accumulated in one call stores its waveform pairs
-        (SCOPE_BAND_EXCLUSIVE) or writes final u8 columns, so the 2 x 256 x W pairs need no zero-fill."""
+        (SCOPE_BAND_EXCLUSIVE) or writes final u8 columns, so the 2 x 256 x W pairs need no zero-fill.
+        additive=True: the caller feeds several tiles per rank through `engine.accumulate_partial`, which ADDS its
+        pairs: zero them as well."""
         for k in self._other_keys():
             self.partial[k].zero_()
+        if additive:
+            self.partial["wave_pairs"].zero_()
 
     def accumulate(self, band, width: Optional[int] = None):
         """band: this rank's rows (rows mode: (h_band, W, 4)) or columns (cols mode: a
@@ -286,11 +290,14 @@ class PeerTiledFrame(TiledFrame):
     def _addresses(self, rank: int, names) -> Dict[str, int]:
         return {key: self._bases[rank] + 4 * self._off[sec] for key, sec in names if sec in self._off}
 
-    def reset(self):
+    def reset(self, additive: bool = False):
         """zero what the next accumulate() ADDS to: histogram and vectorscope partials (the first two sections of the
         allocation, one memset of 260 KB) when those scopes are on.  The waveform pairs are stored, not added
-        (SCOPE_BAND_EXCLUSIVE), or not used at all (column bands): no zero-fill."""
-        if self._other_keys():
+        (SCOPE_BAND_EXCLUSIVE), or not used at all (column bands): no zero-fill - unless the caller feeds several
+        tiles per rank through `engine.accumulate_partial` (additive=True: one memset over all three sections)."""
+        if additive:
+            self._buf[:self._off["out_wave"]].zero_()
+        elif self._other_keys():
             self._buf[:self._off["wave_pairs"]].zero_()
 
     def accumulate(self, band, width: Optional[int] = None):

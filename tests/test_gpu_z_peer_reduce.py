@@ -134,7 +134,7 @@ def test_peer_tiled_frame_single_rank(engine, oracle, pkg):
     tiled = pkg.sharding.PeerTiledFrame(engine, W, H, st, mode="rows")
     assert tiled.world == 1 and tiled.my_band == (0, H) and not tiled.two_shot
     for _ in range(2):                                   # twice: reset() must give a clean second frame
-        tiled.reset()
+        tiled.reset(additive=True)                       # accumulate_partial ADDS its waveform pairs
         for y0, y1 in BANDS:
             engine.accumulate_partial(d[y0:y1], tiled.partial, x_offset=0, full_width=W, settings=st)
         out = tiled.reduce_and_finalize()
