@@ -15,7 +15,7 @@ all: product oracle
 
 product: $(LIBDIR)/libscope_b200.so $(LIBDIR)/libcm_shim.so
 
-$(LIBDIR)/libscope_b200.so: Makefile $(PKG)/csrc/exports.map $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h
+$(LIBDIR)/libscope_b200.so: Makefile $(PKG)/csrc/exports.map $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_fused_v3.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
 
@@ -31,43 +31,32 @@ clean:
 	$(MAKE) -C oracle clean
 .PHONY: all product oracle clean
 
-# A/B builds for kernel work (tools/run_ab.sh runs the GPU parity tests on, and benches, every
-# variants_tmp/*.so through SCOPE_LIB).  `python tools/sass_budget.py variants_tmp/X.so` gives the static
-# instruction budget of a variant's steady-state loop without a GPU.  Names ending in _x are built with
-# SCOPE_EXPERIMENT: their two-plane (surface mode) rings do not fit, run_ab.sh skips those tests for them.
+# A/B builds for kernel work: `SCOPE_LIB=$PWD/variants_tmp/X.so python bench.py ...` (tools/gpu_call7.sh runs the GPU
+# parity tests on, and benches, every variants_tmp/*.so).  What round 2 measured with them: profiles/r02/ab_v3/.
+#   v3off          the general kernel serves the headline combination too (the round-1 path)
+#   v3_scalar      scope_fused_kernel_v3 with scalar FFMA / FADD instead of the f32x2 forms
+#   v3_pf0         no L2 prefetch ahead of the TMA loads
+#   v3_nop         DIAGNOSTIC (results wrong by construction): ring, end-of-strip write-out and flushes only, no accumulation
+#   v3_noload      DIAGNOSTIC: no TMA at all, the consumers accumulate whatever the stages hold
+#   v3_s1/_s2/_s3  DIAGNOSTIC: without the column-bin adds / the vectorscope adds / both (addresses still computed)
+#   v3_red         DIAGNOSTIC: vectorscope adds without return value (saturation of flat content then wrong)
+#   w8, straight, nopipe: build flags of the general kernel that tests/test_kernel_emulation.py still covers
 VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
-VARIANTS = dephase wide_dephase wide_straight_dephase w8_dephase wide wide_straight immcoef w16n8_immcoef_r120_x w16n8_straight_immcoef_r120_x w8 w12n8_x w12n6_x w16n6_x w16n6_straight_x w16n8_r120_x w16n8_straight_r120_x w16n6_straight_r120_x r120 straight w8_straight w12n8_straight_x ballot w8_straight_ballot deepring nopipe rawflat w8_deepring nofaddr nodefer
+VARIANTS = v3off v3_scalar v3_pf0 v3_nop v3_noload v3_s1 v3_s2 v3_s3 v3_red w8 straight nopipe
+FLAGS_v3off = -DSCOPE_V3=0
+FLAGS_v3_scalar = -DSCOPE_V3_FFMA2=0
+FLAGS_v3_pf0 = -DSCOPE_V3_L2_AHEAD=0
+FLAGS_v3_nop = -DSCOPE_V3_NOP
+FLAGS_v3_noload = -DSCOPE_V3_NOLOAD
+FLAGS_v3_s1 = -DSCOPE_V3_SKIP=1
+FLAGS_v3_s2 = -DSCOPE_V3_SKIP=2
+FLAGS_v3_s3 = -DSCOPE_V3_SKIP=3
+FLAGS_v3_red = -DSCOPE_V3_SKIP=4
 FLAGS_w8 = -DSCOPE_TMA_WARPS=8
-FLAGS_dephase = -DSCOPE_DEPHASE=1
-FLAGS_wide_dephase = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_DEPHASE=1
-FLAGS_wide_straight_dephase = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1 -DSCOPE_DEPHASE=1
-FLAGS_w8_dephase = -DSCOPE_TMA_WARPS=8 -DSCOPE_DEPHASE=1
-FLAGS_immcoef = -DSCOPE_IMMCOEF=1
-FLAGS_wide = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1
-FLAGS_wide_straight = -DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1
-FLAGS_w16n8_immcoef_r120_x = -DSCOPE_IMMCOEF=1 -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_MAXNREG=120
-FLAGS_w16n8_straight_immcoef_r120_x = -DSCOPE_IMMCOEF=1 -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_STRAIGHT=1 -DSCOPE_MAXNREG=120
-FLAGS_w12n8_x = -DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=96
-FLAGS_w12n6_x = -DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=72
-FLAGS_w16n6_x = -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=96
-FLAGS_w16n6_straight_x = -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=96 -DSCOPE_STRAIGHT=1
-FLAGS_w16n6_straight_r120_x = -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=96 -DSCOPE_STRAIGHT=1 -DSCOPE_MAXNREG=120
-FLAGS_w16n8_r120_x = -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_MAXNREG=120
-FLAGS_w16n8_straight_r120_x = -DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_STRAIGHT=1 -DSCOPE_MAXNREG=120
-FLAGS_r120 = -DSCOPE_MAXNREG=120
-FLAGS_deepring = -DSCOPE_DEEP_RING=1
-FLAGS_nopipe = -DSCOPE_PIPELINE=0
-FLAGS_rawflat = -DSCOPE_RAWFLAT=1
 FLAGS_straight = -DSCOPE_STRAIGHT=1
-FLAGS_ballot = -DSCOPE_BALLOT=1
-FLAGS_w8_straight_ballot = -DSCOPE_BALLOT=1 -DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8
-FLAGS_w8_straight = -DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8
-FLAGS_w12n8_straight_x = -DSCOPE_STRAIGHT=1 -DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=96
-FLAGS_w8_deepring = -DSCOPE_TMA_WARPS=8 -DSCOPE_DEEP_RING=1
-FLAGS_nofaddr = -DSCOPE_FADDR=0
-FLAGS_nodefer = -DSCOPE_DEFER=0
+FLAGS_nopipe = -DSCOPE_PIPELINE=0
 variants: $(VARIANTS:%=variants_tmp/%.so)
-variants_tmp/%.so: $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h Makefile
+variants_tmp/%.so: $(PKG)/csrc/scope_ffi.cu $(PKG)/csrc/scope_kernels.cuh $(PKG)/csrc/scope_fused_v3.cuh $(PKG)/csrc/scope_kernels_experiments.cuh $(PKG)/csrc/scope_peer_reduce.cuh include/scope_ffi.h Makefile
 	@mkdir -p variants_tmp
 	$(VARIANT) $(FLAGS_$*) -o $@
 .PHONY: variants

@@ -361,10 +361,11 @@ def run_b200_arm(args):
         step()
     barrier()
     # sanity: every pixel of every frame was counted (alpha is 255 everywhere in the synthetic batch)
-    if "hist" in out:
+    diagnostic = bool(os.environ.get("SCOPE_BENCH_DIAGNOSTIC"))   # kernel A/B builds that compute nothing (ring-only timing)
+    if "hist" in out and not diagnostic:
         hsum = out["hist"].to(torch.int64).sum(dim=1)
         assert bool((hsum == 3 * W * H).all()), "histogram totals are wrong"
-    if "vscope" in out:
+    if "vscope" in out and not diagnostic:
         assert bool((out["vscope"].amax(dim=(1, 2)) > 0).all())
     # parity of the TIMED batch (outside the timed region): frames 0..3 = one of every content class of the mixed
     # batch, bit for bit against the reference's own compiled loops (oracle/_ref; the oracle port if absent)

@@ -266,6 +266,8 @@ void scope_host_free(void *p);
 /* test hook, not part of the drop-in surface: the kernels' own RGB->YUV transform for
  * all 2^24 colours, d_out[r<<16|g<<8|b] = u | y<<8 | v<<16 (device pointer). */
 int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
+/* the same for the headline kernel's own form of the transform (scope_fused_v3.cuh): d_out[..] = u | v<<8 */
+int scope_debug_uv_table_v3(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
 
 /* size helpers */
 size_t scope_wave_bytes(uint32_t width);          /* 256*width*4 */

@@ -131,7 +131,10 @@ void decode_components(uint32_t comp, int &src, uint32_t &mask)
 typedef void (*TmaKernel)(const StripParams, const CUtensorMap, const CUtensorMap);
 typedef void (*LdgKernel)(const StripParams);
 
+typedef void (*V3Kernel)(const StripParams, const CUtensorMap);
+
 struct KernelChoice {
+	V3Kernel v3 = nullptr; // the headline combination's own kernel (scope_fused_v3.cuh)
 	TmaKernel tma = nullptr;
 	LdgKernel ldg = nullptr;
 	int smem = 0, threads = 0;
@@ -330,7 +333,16 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 #endif
 
 	KernelChoice k;
-	if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
+	// fused mode, RGB column bins for all three channels, final u8 waveform, vectorscope: scope_fused_kernel_v3
+	const bool v3 = SCOPE_V3 && use_tma && !rq.surface && rq.src == SRC_RGB && rq.vscope && rq.bins_mask == 7u &&
+			rq.wave_mask == 7u && (rq.hist_mask == 7u || rq.hist_mask == 0u) && rq.partial == 0 &&
+			rq.n_wave_copies == 0 && rq.wave != nullptr;
+	if (v3) {
+		k.v3 = rq.colorspace == 1 ? scope_fused_kernel_v3<1> : scope_fused_kernel_v3<2>;
+		k.smem = V3::kTotal;
+		k.threads = V3::kThreads;
+		k.tile_rows = V3::kTileRows;
+	} else if (!pick_kernel(rq.src, rq.vscope, rq.surface, use_tma, rq.colorspace, k))
 		return fail(ctx, SCOPE_ERR_INVALID, "no kernel for this scope combination");
 
 	CUtensorMap map_rgb, map_yuv;
@@ -352,7 +364,7 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	}
 
 	// the opt-in to large dynamic shared memory and the occupancy of a kernel never change: asked once
-	const void *fn = use_tma ? (const void *)k.tma : (const void *)k.ldg;
+	const void *fn = k.v3 ? (const void *)k.v3 : use_tma ? (const void *)k.tma : (const void *)k.ldg;
 	int ctas_per_sm = 0;
 	for (const auto &f : ctx->kernel_facts)
 		if (f.fn == fn)
@@ -395,7 +407,9 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 		}
 		CU_TRY(ctx, cudaEventRecord(ev.first, stream));
 	}
-	if (use_tma)
+	if (k.v3)
+		k.v3<<<grid, k.threads, k.smem, stream>>>(P, map_rgb);
+	else if (use_tma)
 		k.tma<<<grid, k.threads, k.smem, stream>>>(P, map_rgb, map_yuv);
 	else
 		k.ldg<<<grid, k.threads, k.smem, stream>>>(P);
@@ -1331,6 +1345,23 @@ int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out /* dev
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	DeviceGuard guard(ctx->device);
 	yuv_table_kernel<<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(coef_for(colorspace), d_out);
+	CU_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return SCOPE_OK;
+}
+
+// test hook: the transform of scope_fused_kernel_v3 (funnel shift + FADD2 / FFMA2 division) over all 2^24 colours,
+// d_out[r<<16|g<<8|b] = u | v<<8
+int scope_debug_uv_table_v3(scope_ctx *ctx, int colorspace, uint32_t *d_out /* device, 1<<24 u32 */, void *stream)
+{
+	if (!ctx || !d_out)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	if (colorspace == 1)
+		uv_table_kernel_v3<1><<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(d_out);
+	else
+		uv_table_kernel_v3<2><<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(d_out);
 	CU_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
 	return SCOPE_OK;

@@ -215,6 +215,9 @@ struct StripParams {
 	uint32_t *vscope_acc;     // [n][65536] u32, zeroed
 	unsigned long long hist_stride, wave_stride, vscope_stride; // elements between frames
 	uint8_t *wave_copies[kMaxWaveCopies]; // column-band sharding: every rank's image gets this rank's columns
+	uint32_t rt_zero;         // always 0, but only known at run time: the consumers AND it with the pixels they loaded
+	                          // and add it to the address of the "stage is free" arrive, so that ptxas must keep the
+	                          // arrive behind the arrival of the data (a `mov 0` inside inline PTX is folded by ptxas)
 	Coef coef;
 };
 
@@ -297,6 +300,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
 		     " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
 		     "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+		     : "memory");
+#endif
+}
+// L2 prefetch of a tile (no shared-memory destination, no completion): issued a few tiles ahead of the load so that
+// the load itself finds its lines in L2 - the ring then covers the L2 latency instead of the HBM latency
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int x, int y, int z)
+{
+#ifdef SCOPE_EMULATE
+	(void)map; (void)x; (void)y; (void)z;
+#else
+	asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
 		     : "memory");
 #endif
 }
@@ -1312,8 +1326,7 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	coef.ku = P.coef.ku;
 	coef.ky = P.coef.ky;
 	coef.kv = P.coef.kv;
-	uint32_t zero; // a 0 the compiler cannot see through (used to build data dependencies)
-	zero = opaque_zero();
+	const uint32_t zero = P.rt_zero; // a 0 the compiler cannot see through (used to build data dependencies)
 	uint32_t stage = 0, phase = 0, qr = 0;
 	uint32_t cur_frame = 0xFFFFFFFFu;
 
@@ -1580,6 +1593,10 @@ __global__ void SCOPE_TMA_BOUNDS
 	tma_consume<L, SRC, VSCOPE, SURFACE, RPW, NW, SRC != SRC_NONE, VSCOPE, CS>(P, smem, smem_base, chunk_q, bar_full,
 										  bar_empty, warp * RPW, warp, lane, tid);
 }
+
+} // namespace scope
+#include "scope_fused_v3.cuh" // the headline combination (fused mode, RGB bins + vectorscope) as its own kernel
+namespace scope {
 
 // the kernels that were measured and not adopted (row-group consumer, warp-specialised kernel): A/B builds
 // (-DSCOPE_EXPERIMENT) and the CPU emulator only; the shipped library does not carry them

@@ -394,6 +394,15 @@ class ScopeEngine:
                                                          C.byref(mi) if mi is not None else None, C.c_void_p(stream)))
         return local_out
 
+    def debug_uv_table_v3(self, colorspace: int):
+        """test hook: U | V << 8 of the headline kernel's own transform for all 2^24 colours"""
+        import torch
+
+        out = torch.empty(1 << 24, dtype=torch.int32, device="cuda")
+        self.ctx.check(self.lib.scope_debug_uv_table_v3(self.ctx.handle, colorspace, out.data_ptr(),
+                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
     # test hook
     def debug_yuv_table(self, colorspace: int):
         import torch

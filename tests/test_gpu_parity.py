@@ -115,6 +115,18 @@ def test_transform_exhaustive(engine, oracle):
         assert bad.size == 0, f"colorspace {cs}: {bad.size} colours differ, first {bad[:5]}"
 
 
+def test_transform_exhaustive_v3(engine, oracle):
+    """the headline kernel's form of the transform (integer sums, division by 10^6 as funnel shift + f32x2 add +
+    f32x2 fused multiply-add, scope_fused_v3.cuh) for all 2^24 colours == the pinned oracle"""
+    for cs in (1, 2):
+        exp, clamp = oracle.rgb_to_yuv_table(cs)
+        assert not clamp
+        exp_uv = (exp & 0xFF) | ((exp >> 16) & 0xFF) << 8
+        got = engine.debug_uv_table_v3(cs).cpu().numpy().view(np.uint32)
+        bad = np.nonzero(got != exp_uv)[0]
+        assert bad.size == 0, f"colorspace {cs}: {bad.size} colours differ, first {bad[:5]}"
+
+
 def test_device_batch(engine, oracle, pkg):
     import torch
     fr = pkg.frames

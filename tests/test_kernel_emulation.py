@@ -14,10 +14,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tools", "simt", "_build")
 SOURCES = [os.path.join(ROOT, "tools", "simt", f) for f in ("cuda_emul.h", "emul_main.cpp", "build.sh")] + \
-          [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", f) for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh")]
-VARIANTS = ["default", "dephase", "wide_dephase", "wide_straight_dephase", "w8_dephase", "wide", "wide_straight", "w8", "w12n6", "w12n8", "w16n6_straight", "w16n8", "immcoef", "w16n8_straight_immcoef", "ballot", "w8_straight_ballot", "straight", "w8_straight", "rawflat", "deepring", "nopipe", "base"]
+          [os.path.join(ROOT, "obs-color-monitor_b200", "csrc", f)
+           for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh", "scope_fused_v3.cuh")]
+# build-flag sets of the general kernel that are still exercised (round 2 measured the others and dropped them:
+# profiles/r02/ab_round2.md); "default" also carries scope_fused_kernel_v3, the headline combination's own kernel
+VARIANTS = ["default", "w8", "w12n6", "straight", "w8_straight", "wide", "nopipe", "base"]
 SRC_NONE, SRC_RGB, SRC_YUV = 0, 1, 2
-K_TMA, K_LDG, K_GROUP = 0, 1, 2
+K_TMA, K_LDG, K_GROUP, K_V3 = 0, 1, 2, 3
 
 
 class Request(C.Structure):
@@ -128,20 +131,20 @@ def test_fused_all_scopes_every_variant(emul_libs, oracle, pkg, variant):
         check(oracle, frames, out, yuv, 0x07, 0x07, True, f"{variant} ({lib.emul_build_flags().decode()}) seed {seed}")
 
 
-@pytest.mark.parametrize("variant", ["default", "w8_straight", "w12n6", "immcoef", "wide", "dephase", "wide_dephase"])
+@pytest.mark.parametrize("variant", ["default", "w8_straight", "w12n6", "wide"])
 def test_other_kernels_and_modes(emul_libs, oracle, pkg, variant):
     lib = emul_libs[variant]
     fr = pkg.frames
     frames = np.stack([fr.alpha_stripes(45, 131, 7), fr.natural(45, 131, 8)])
     yuv = [oracle.rgb_to_yuv(f, 1) for f in frames]
     yuv_arr = np.ascontiguousarray(np.stack(yuv))
-    surface_ok = variant in ("default", "immcoef", "wide")   # the _x builds' two-plane ring does not fit (SCOPE_EXPERIMENT)
+    surface_ok = variant in ("default", "wide")   # the _x builds' two-plane ring does not fit (SCOPE_EXPERIMENT)
     cases = [dict(hist_comp=0x70, wave_comp=0x20, vscope=True),                    # fused, YUV bins + vectorscope
              dict(hist_comp=0x07, wave_comp=0x05, vscope=False),                   # no vectorscope: 2 CTAs per SM kernel
              dict(hist_comp=0x00, wave_comp=0x00, vscope=True),                    # vectorscope only
              dict(hist_comp=0x50, wave_comp=0x00, vscope=False)]                   # histogram only, two channels
     for kw in cases:
-        for kernel in (K_TMA, K_LDG) + ((K_GROUP,) if variant in ("default", "immcoef") else ()):
+        for kernel in (K_TMA, K_LDG) + ((K_GROUP,) if variant == "default" else ()):
             out = run(lib, frames, colorspace=1, kernel=kernel, ctas=3, seed=5, **kw)
             check(oracle, frames, out, yuv, kw["hist_comp"], kw["wave_comp"], kw["vscope"], f"{variant} fused {kw} kernel {kernel}")
     if surface_ok:
@@ -155,7 +158,7 @@ def test_other_kernels_and_modes(emul_libs, oracle, pkg, variant):
                       f"{variant} surface {kw} kernel {kernel}")
 
 
-@pytest.mark.parametrize("variant", ["default", "w8", "straight", "rawflat", "wide_straight"])
+@pytest.mark.parametrize("variant", ["default", "w8", "straight"])
 def test_saturation_and_flat_blocks(emul_libs, oracle, pkg, variant):
     """a solid frame: one vectorscope bin takes every pixel (more than the 0x8000 a half-word bin may hold before
     adds are taken back), waveform bins saturate at 255, the flat-block path is the one that runs; plus a frame
@@ -173,7 +176,7 @@ def test_saturation_and_flat_blocks(emul_libs, oracle, pkg, variant):
     assert out[2][0].max() == 255 and out[1][0].max() == 255
 
 
-@pytest.mark.parametrize("variant", ["default", "ballot", "w8_straight_ballot"])
+@pytest.mark.parametrize("variant", ["default"])
 def test_almost_flat_blocks(emul_libs, oracle, pkg, variant):
     """screen-like content: a flat background with text in it.  Most blocks are not flat but most lanes sit on
     the background's bin - the case SCOPE_BALLOT aggregates (and the shipped kernel must get right the slow way);
@@ -233,7 +236,7 @@ def test_pitched_rows_and_tile_sharded_frames(emul_libs, oracle, pkg, variant):
     assert np.array_equal(np.minimum(acc[0], 255).astype(np.uint8).reshape(256, 256), oracle.vectorscope(y))
 
 
-@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight", "w16n8", "wide"])
+@pytest.mark.parametrize("variant", ["default", "w12n6", "w8_straight", "wide"])
 def test_extreme_geometries(emul_libs, oracle, pkg, variant):
     """one pixel, one row, one column, a narrow tall strip, exactly one tile, one row more than a tile"""
     lib = emul_libs[variant]
@@ -291,7 +294,7 @@ def test_emulator_catches_injected_bugs(oracle, pkg, tmp_path):
     for name, (good, bad) in bugs.items():
         d = tmp_path / name
         d.mkdir()
-        for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh"):
+        for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh", "scope_fused_v3.cuh"):
             shutil.copy(os.path.join(csrc, f), d / f)
         text = (d / "scope_kernels.cuh").read_text()
         assert text.count(good) == 1, f"the line the '{name}' bug replaces has changed"
@@ -309,6 +312,95 @@ def test_emulator_catches_injected_bugs(oracle, pkg, tmp_path):
         for seed, land in ((1, 30), (2, 2), (3, 10)):
             try:
                 out = run(lib, frames, seed=seed, land=land)
+                check(oracle, frames, out, yuv, 0x07, 0x07, True, name)
+            except AssertionError:
+                caught += 1
+        assert caught > 0, f"injected bug '{name}' went unnoticed"
+
+
+# ---------------------------------------------------------------------------
+# scope_fused_kernel_v3 (csrc/scope_fused_v3.cuh): the headline combination's own kernel
+# ---------------------------------------------------------------------------
+def test_v3_headline_batch(emul_libs, oracle, pkg):
+    """4 frames x 3 strips (the last one 6 pixels wide), partial last tile, transparent pixels, both colour spaces,
+    several CTAs sharing the chunk counter, TMA loads that land promptly / late / almost never"""
+    lib = emul_libs["default"]
+    frames = small_batch(pkg)
+    for cs in (2, 1):
+        yuv = [oracle.rgb_to_yuv(f, cs) for f in frames]
+        for seed, land, ctas in ((1, 30, 2), (2, 3, 3), (3, 60, 1)):
+            out = run(lib, frames, kernel=K_V3, seed=seed, land=land, ctas=ctas, colorspace=cs)
+            check(oracle, frames, out, yuv, 0x07, 0x07, True, f"v3 cs {cs} seed {seed}")
+    out = run(lib, frames, kernel=K_V3, hist_comp=0, seed=9)              # waveform + vectorscope, no histogram
+    check(oracle, frames, out, [oracle.rgb_to_yuv(f, 2) for f in frames], 0, 0x07, True, "v3 without histogram")
+
+
+def test_v3_saturation_flat_and_almost_flat(emul_libs, oracle, pkg):
+    """solid frame (one vectorscope half beyond 0x8000: adds taken back; the flat-block path), a solid frame with
+    specks and transparent pixels, and screen-like content where most blocks are flat and some are not"""
+    lib = emul_libs["default"]
+    w, h = 96, 800                       # 76 800 pixels on one bin > 65 535
+    solid = pkg.frames.solid(w, h, (200, 17, 90, 255))
+    speck = solid.copy()
+    speck[::37, ::11] = (3, 250, 128, 255)
+    speck[5::53, 7::13, 3] = 0
+    frames = np.stack([solid, speck])
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    out = run(lib, frames, kernel=K_V3, ctas=1, seed=11)
+    check(oracle, frames, out, yuv, 0x07, 0x07, True, "v3 solid")
+    assert out[2][0].max() == 255 and out[1][0].max() == 255
+    ui = np.stack([pkg.frames.ui(96, 400, 1), pkg.frames.ui(96, 400, 2)])
+    ui[1, 100:140, 10:50] = pkg.frames.random(40, 40, 3)
+    ui[1, ::29, ::7, 3] = 0
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in ui]
+    for seed, land in ((21, 30), (22, 3)):
+        out = run(lib, ui, kernel=K_V3, ctas=2, seed=seed, land=land)
+        check(oracle, ui, out, yuv, 0x07, 0x07, True, f"v3 ui seed {seed}")
+
+
+def test_v3_extreme_geometries(emul_libs, oracle, pkg):
+    """one row, one tile exactly (23 warps x 4 rows = 92), one row more, fewer rows than one warp takes, narrow strips"""
+    lib = emul_libs["default"]
+    for w, h in ((4, 1), (36, 1), (4, 97), (8, 300), (32, 92), (64, 93), (32, 63), (40, 3)):
+        f = np.ascontiguousarray(pkg.frames.random(w, h, seed=w * 1000 + h)[None])
+        yuv = [oracle.rgb_to_yuv(f[0], 2)]
+        out = run(lib, f, kernel=K_V3, ctas=2, seed=w + h)
+        check(oracle, f, out, yuv, 0x07, 0x07, True, f"v3 {w}x{h}")
+
+
+def test_v3_emulator_catches_injected_bugs(oracle, pkg, tmp_path):
+    """one deliberate bug each in a copy of scope_fused_v3.cuh: the flush's division by 260 off by one in its magic
+    number, the vectorscope index bias for V - 16 missing, one arrival too few on the "empty" barriers"""
+    import shutil
+    csrc = os.path.join(ROOT, "obs-color-monitor_b200", "csrc")
+    bugs = {
+        "div260": ("const uint32_t vq = ((idx >> 2) * 64528u) >> 22;", "const uint32_t vq = ((idx >> 2) * 64000u) >> 22;"),
+        "vbias": ("constexpr uint32_t kV3UBias = 65536u - V3::kVStride * V3::kVMin;", "constexpr uint32_t kV3UBias = 65536u - V3::kVStride * (V3::kVMin - 1);"),
+        "arrivals": ("mbar_init(bar_empty + 8 * s, V3::kWarps);", "mbar_init(bar_empty + 8 * s, V3::kWarps - 1);"),
+    }
+    frames = small_batch(pkg)
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+    procs = {}
+    for name, (good, bad) in bugs.items():
+        d = tmp_path / name
+        d.mkdir()
+        for f in ("scope_kernels.cuh", "scope_kernels_experiments.cuh", "scope_fused_v3.cuh"):
+            shutil.copy(os.path.join(csrc, f), d / f)
+        text = (d / "scope_fused_v3.cuh").read_text()
+        assert text.count(good) == 1, f"the line the '{name}' bug replaces has changed"
+        (d / "scope_fused_v3.cuh").write_text(text.replace(good, bad))
+        procs[name] = subprocess.Popen(
+            ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DSCOPE_EMULATE", "-include",
+             os.path.join(ROOT, "tools", "simt", "cuda_emul.h"), f"-I{d}", os.path.join(ROOT, "tools", "simt", "emul_main.cpp"),
+             "-o", str(d / "lib.so")])
+    for name, p in procs.items():
+        assert p.wait() == 0
+        lib = C.CDLL(str(tmp_path / name / "lib.so"))
+        lib.emul_run.argtypes = [C.POINTER(Request)]
+        caught = 0
+        for seed, land in ((1, 30), (2, 2)):
+            try:
+                out = run(lib, frames, kernel=K_V3, seed=seed, land=land)
                 check(oracle, frames, out, yuv, 0x07, 0x07, True, name)
             except AssertionError:
                 caught += 1

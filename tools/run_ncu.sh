@@ -5,9 +5,9 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 TAG=${1:-r02a}; FRAMES=${2:-64}
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:scope_strip -s 3 -c 1 \
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:"scope_strip|scope_fused" -s 3 -c 1 \
   -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --frames-per-gpu $FRAMES --no-e2e --no-cpu-baseline --no-config4 > gpurun_out/ncu_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_$TAG.log | cut -c1-200
-timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scope_strip|finalize|hist_max" -s 9 -c 24 --csv \
+timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scope_strip|scope_fused|finalize|hist_max" -s 9 -c 24 --csv \
   --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline --no-config4 > gpurun_out/launches_$TAG.log 2>&1
 ls -la gpurun_out/prof_$TAG.ncu-rep gpurun_out/launches_$TAG.csv

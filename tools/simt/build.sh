@@ -14,23 +14,9 @@ pids=""
 build default "" & pids="$pids $!"
 build w8 "-DSCOPE_TMA_WARPS=8" & pids="$pids $!"
 build w12n6 "-DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=72" & pids="$pids $!"
-build w12n8 "-DSCOPE_EXPERIMENT -DSCOPE_TMA_WARPS=12 -DSCOPE_TILE_ROWS=96" & pids="$pids $!"
-build w16n6_straight "-DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=96 -DSCOPE_STRAIGHT=1" & pids="$pids $!"
-build ballot "-DSCOPE_BALLOT=1" & pids="$pids $!"
-build w8_straight_ballot "-DSCOPE_BALLOT=1 -DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8" & pids="$pids $!"
-build w16n8 "-DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128" & pids="$pids $!"
-build immcoef "-DSCOPE_IMMCOEF=1" & pids="$pids $!"
-build w16n8_straight_immcoef "-DSCOPE_EXPERIMENT -DSCOPE_TILE_ROWS=128 -DSCOPE_STRAIGHT=1 -DSCOPE_IMMCOEF=1" & pids="$pids $!"
 build wide "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1" & pids="$pids $!"
-build wide_straight "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1" & pids="$pids $!"
 build straight "-DSCOPE_STRAIGHT=1" & pids="$pids $!"
-build dephase "-DSCOPE_DEPHASE=1" & pids="$pids $!"
-build wide_dephase "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_DEPHASE=1" & pids="$pids $!"
-build w8_dephase "-DSCOPE_TMA_WARPS=8 -DSCOPE_DEPHASE=1" & pids="$pids $!"
-build wide_straight_dephase "-DSCOPE_WIDE_FUSED=1 -DSCOPE_IMMCOEF=1 -DSCOPE_STRAIGHT=1 -DSCOPE_DEPHASE=1" & pids="$pids $!"
 build w8_straight "-DSCOPE_STRAIGHT=1 -DSCOPE_TMA_WARPS=8" & pids="$pids $!"
-build rawflat "-DSCOPE_RAWFLAT=1" & pids="$pids $!"
-build deepring "-DSCOPE_DEEP_RING=1" & pids="$pids $!"
 build nopipe "-DSCOPE_PIPELINE=0" & pids="$pids $!"
 build base "-DSCOPE_LDSM=0 -DSCOPE_XORSWZ=0 -DSCOPE_DEFER=0 -DSCOPE_FADDR=0 -DSCOPE_FAST_EMIT=0" & pids="$pids $!"
 rc=0

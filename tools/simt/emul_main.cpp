@@ -87,7 +87,12 @@ const Launch *g_launch;
 void thread_entry()
 {
 	const Launch &l = *g_launch;
-	if (l.surf)
+	if (l.kernel == 3) { // scope_fused_kernel_v3: the headline combination's own kernel
+		if (l.colorspace == 1)
+			scope_fused_kernel_v3<1>(l.P, l.map_rgb);
+		else
+			scope_fused_kernel_v3<2>(l.P, l.map_rgb);
+	} else if (l.surf)
 		dispatch2<true>(l);
 	else
 		dispatch2<false>(l);
@@ -183,7 +188,14 @@ extern "C" int emul_run(EmulRequest *rq)
 
 	const bool need_rgb = !l.surf || l.src == SRC_RGB;
 	const bool need_yuv = l.surf && (l.src == SRC_YUV || l.vs);
-	const int tile_rows = l.surf ? tile_rows_for<true>(l.src, l.vs) : tile_rows_for<false>(l.src, l.vs);
+	if (rq->kernel == 3 && !(l.src == SRC_RGB && l.vs && !l.surf && P.bins_mask == 7u && P.wave_mask == 7u &&
+				 (P.hist_mask == 7u || P.hist_mask == 0u) && P.partial == 0u)) {
+		snprintf(rq->error, sizeof rq->error, "kernel 3 serves fused RGB bins + vectorscope only");
+		return 1;
+	}
+	const int tile_rows = rq->kernel == 3 ? V3::kTileRows
+			      : l.surf      ? tile_rows_for<true>(l.src, l.vs)
+					    : tile_rows_for<false>(l.src, l.vs);
 	if (need_rgb)
 		make_map(l.map_rgb, rq->rgb, rq->width, rq->linesize, rq->height, rq->n_frames, rq->frame_stride, tile_rows);
 	if (need_yuv)
@@ -203,10 +215,13 @@ extern "C" int emul_run(EmulRequest *rq)
 		uint32_t ch = P.items / (grid * 6u);
 		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
 		P.chunk_counter = &chunk_counter;
-		threads = (rq->kernel == 2 ? kGroupWarps
-					   : (l.surf ? tma_warps_for<true>(l.src, l.vs) : tma_warps_for<false>(l.src, l.vs))) * 32 + 32;
+		threads = (rq->kernel == 3   ? V3::kWarps
+			   : rq->kernel == 2 ? kGroupWarps
+					     : (l.surf ? tma_warps_for<true>(l.src, l.vs) : tma_warps_for<false>(l.src, l.vs))) * 32 + 32;
 	}
-	const int smem = l.surf ? smem_for<true>(l.src, l.vs, rq->kernel) : smem_for<false>(l.src, l.vs, rq->kernel);
+	const int smem = rq->kernel == 3 ? V3::kTotal
+			 : l.surf       ? smem_for<true>(l.src, l.vs, rq->kernel)
+					: smem_for<false>(l.src, l.vs, rq->kernel);
 	if (smem > (int)emul::kSmemBytes) {
 		snprintf(rq->error, sizeof rq->error, "kernel needs %d bytes of shared memory: does not fit an SM", smem);
 		return 1;
