@@ -20,8 +20,8 @@ $(LIBDIR)/libscope_b200.so: Makefile $(PKG)/csrc/exports.map $(PKG)/csrc/scope_f
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
 
 $(LIBDIR)/libcm_shim.so: $(PKG)/csrc/cm_shim.c include/cm_shim.h include/scope_ffi.h $(LIBDIR)/libscope_b200.so
-	gcc -std=gnu11 -O2 -g -fPIC -Wall -Wextra -shared -o $@ $(PKG)/csrc/cm_shim.c -Iinclude \
-	    -L$(LIBDIR) -lscope_b200 -Wl,-rpath,'$$ORIGIN' -lpthread -lm
+	gcc -std=gnu11 -O2 -g -fPIC -Wall -Wextra -shared -o $@ $(PKG)/csrc/cm_shim.c -Iinclude -I/usr/local/cuda/include \
+	    -L$(LIBDIR) -lscope_b200 -Wl,-rpath,'$$ORIGIN' -lpthread -lm -ldl
 
 oracle:
 	$(MAKE) -C oracle

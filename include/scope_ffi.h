@@ -101,8 +101,20 @@ struct scope_params {
 	/* display mapping; 0 = not requested */
 	int32_t wave_intensity;
 	int32_t vscope_intensity;
-	uint32_t reserved[3];
+	/* point-downsample before the scopes, the reference's `target_scale` (1..128, default 2: common.c:88-90,
+	 * histogram.c:166, waveform.c:113, vectorscope.c:157): 0 or 1 = none.  The surface is the FULL-SIZE target;
+	 * the scopes see width / target_scale x height / target_scale pixels (common.c:249-250), pixel (x, y) of
+	 * them being the source pixel (x s + s / 2, y s + s / 2) - the texel a point-sampled render of the target
+	 * into the smaller texrender picks.  Output widths (waveform) are the scaled width. */
+	uint32_t target_scale;
+	/* how SCOPE_MODE_FUSED evaluates data/common.effect:23-43 (the transform is a float shader
+	 * in the reference and nothing pins its rounding): */
+	uint32_t xform;
+	uint32_t reserved[1];
 };
+#define SCOPE_XFORM_EXACT 0       /* the exact value of the expression, rounded like a UNORM8 target (the default) */
+#define SCOPE_XFORM_FP32_STRICT 1 /* fp32, every product and sum rounded separately, left to right, no FMA
+                                     (SURVEY.md 8(c)'s draft; differs on < 0.003 % of the colours, by one step) */
 
 /* host result buffers; NULL members are skipped */
 struct scope_out_host {
@@ -268,6 +280,8 @@ void scope_host_free(void *p);
 int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
 /* the same for the headline kernel's own form of the transform (scope_fused_v3.cuh): d_out[..] = u | v<<8 */
 int scope_debug_uv_table_v3(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
+/* the same for SCOPE_XFORM_FP32_STRICT: d_out[..] = u | y<<8 | v<<16 */
+int scope_debug_yuv_table_strict(scope_ctx *ctx, int colorspace, uint32_t *d_out, void *stream);
 
 /* size helpers */
 size_t scope_wave_bytes(uint32_t width);          /* 256*width*4 */

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "scope_abi_version", "scope_ctx_create", "scope_ctx_destroy", "scope_last_error",
     "scope_launch_count", "scope_sm_count", "scope_accumulate_host", "scope_submit_host",
     "scope_wait_host", "scope_ring_input", "scope_accumulate_device", "scope_accumulate_partial", "scope_accumulate_band",
-    "scope_finalize_partial", "scope_finalize_peers", "scope_finalize_multicast", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table", "scope_debug_uv_table_v3",
+    "scope_finalize_partial", "scope_finalize_peers", "scope_finalize_multicast", "scope_host_alloc", "scope_host_free", "scope_debug_yuv_table", "scope_debug_uv_table_v3", "scope_debug_yuv_table_strict",
     "scope_wave_bytes", "scope_partial_wave_words", "scope_profile_enable", "scope_profile_read",
 ]
 
@@ -62,7 +62,9 @@ class Params(C.Structure):
         ("logscale", C.c_int32),
         ("wave_intensity", C.c_int32),
         ("vscope_intensity", C.c_int32),
-        ("reserved", C.c_uint32 * 3),
+        ("target_scale", C.c_uint32),
+        ("xform", C.c_uint32),
+        ("reserved", C.c_uint32 * 1),
     ]
 
 
@@ -165,6 +167,8 @@ def load() -> C.CDLL:
     L.scope_debug_yuv_table.restype = C.c_int
     L.scope_debug_uv_table_v3.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.scope_debug_uv_table_v3.restype = C.c_int
+    L.scope_debug_yuv_table_strict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.scope_debug_yuv_table_strict.restype = C.c_int
     L.scope_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.scope_profile_enable.restype = C.c_int
     L.scope_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]

@@ -4,6 +4,7 @@
 // his_surface_cb / wvs_surface_cb / vss_surface_cb (src/histogram.c:432-450,
 // src/waveform.c:272-289, src/vectorscope.c:248-265) and of the RGB->YUV shader pass
 // (src/common.c:170-221, data/common.effect).  There is no CPU fallback in here.
+#include <nvtx3/nvToolsExt.h> // header-only; ranges named like the reference's profile scopes (common.c:10-21)
 #include "scope_kernels.cuh"
 #include "scope_peer_reduce.cuh"
 #include "../../include/scope_ffi.h"
@@ -265,6 +266,9 @@ struct Request {
 	uint32_t n_wave_copies = 0;
 	uint32_t *vs_acc;
 	size_t vs_stride;
+	// target_scale (width / height above are the SCALED size) and the transform mode: both plain-load kernel only
+	uint32_t scale_x = 1, scale_y = 1;
+	bool strict = false;
 };
 
 int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
@@ -307,6 +311,10 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	P.vscope_acc = rq.vs_acc;
 	P.vscope_stride = rq.vs_stride;
 	P.coef = coef_for(rq.colorspace);
+	P.scale_x = rq.scale_x;
+	P.scale_y = rq.scale_y;
+	P.xform_strict = rq.strict ? 1u : 0u;
+	P.colorspace = rq.colorspace;
 
 	// Loader choice.  TMA can describe the planes if base pointers, pitch and frame stride are
 	// multiples of 16 bytes; everything else (e.g. an ROI crop at an odd column, common.c:272-282)
@@ -320,7 +328,10 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	const char *x0_env = getenv("SCOPE_TMA_X0");
 	allow_x0 = x0_env && x0_env[0] == '1';
 #endif
-	const bool tma_ok = ctx->encode != nullptr && (rq.linesize % 16u) == 0 &&
+	// a scaled pass reads every scale-th pixel (a TMA box would have to start scale / 2 pixels into its row: not
+	// 16-byte aligned), and the fp32-strict transform only exists in the plain-load kernel
+	const bool plain_only = rq.scale_x > 1 || rq.scale_y > 1 || rq.strict;
+	const bool tma_ok = !plain_only && ctx->encode != nullptr && (rq.linesize % 16u) == 0 &&
 			    (rq.n_frames == 1 || (rq.frame_stride % 16u) == 0) &&
 			    (allow_x0 || ((!need_rgb || P.tma_x0_rgb == 0) && (!need_yuv || P.tma_x0_yuv == 0)));
 	bool use_tma = tma_ok && ctx->default_tma;
@@ -456,7 +467,8 @@ int ensure_hist_scratch(scope_ctx *ctx, size_t frames)
 // slot_vs_acc: a ring slot's own vectorscope accumulators (host entry points, n_frames == 1), or NULL:
 // then the context's shared scratch is used, ordered against its previous user through `scratch_free`.
 int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, uint32_t n_frames,
-	       size_t frame_stride, const scope_out_device *out, cudaStream_t stream, uint32_t *slot_vs_acc = nullptr)
+	       size_t frame_stride, const scope_out_device *out, cudaStream_t stream, uint32_t *slot_vs_acc = nullptr,
+	       bool rows_prescaled = false)
 {
 	if (!pr || !s || !out)
 		return fail(ctx, SCOPE_ERR_INVALID, "NULL argument");
@@ -465,6 +477,16 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	if (s->linesize < s->width * 4u)
 		return fail(ctx, SCOPE_ERR_INVALID, "linesize < width*4");
 	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
+	// target_scale: the scopes see the scaled surface (common.c:249-250); scale_y_device = 1 when the caller has
+	// already dropped the rows (the host entry points do that while copying)
+	const uint32_t scale = pr->target_scale > 1 ? pr->target_scale : 1u;
+	if (scale > 128u)
+		return fail(ctx, SCOPE_ERR_INVALID, "target_scale > 128 (common.c:88-90)");
+	const uint32_t sw = s->width / scale, sh = rows_prescaled ? s->height : s->height / scale;
+	if (sw == 0 || sh == 0)
+		return fail(ctx, SCOPE_ERR_INVALID, "surface smaller than target_scale");
+	if (pr->xform != SCOPE_XFORM_EXACT && pr->xform != SCOPE_XFORM_FP32_STRICT)
+		return fail(ctx, SCOPE_ERR_INVALID, "unknown xform");
 	const bool want_hist = (pr->scopes & SCOPE_HIST) && (out->hist_counts || out->hist_max);
 	const bool want_wave = (pr->scopes & SCOPE_WAVE) && (out->wave || out->wave_display);
 	const bool want_vs = (pr->scopes & SCOPE_VSCOPE) && (out->vscope || out->vscope_display);
@@ -505,7 +527,7 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	if (want_hist)
 		CU_TRY(ctx, cudaMemsetAsync(hist, 0, (size_t)n_frames * 1024 * sizeof(uint32_t), stream));
 	if (want_wave && wsrc == SRC_NONE) // components select no plane: the reference leaves zeros
-		CU_TRY(ctx, cudaMemsetAsync(out->wave, 0, (size_t)n_frames * scope_wave_bytes(s->width), stream));
+		CU_TRY(ctx, cudaMemsetAsync(out->wave, 0, (size_t)n_frames * scope_wave_bytes(sw), stream));
 	if (want_vs)
 		CU_TRY(ctx, cudaMemsetAsync(vs_acc, 0, (size_t)n_frames * 65536 * sizeof(uint32_t), stream));
 
@@ -513,8 +535,11 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	rq.rgb = s->rgb_data;
 	rq.yuv = surface ? s->yuv_data : nullptr;
 	rq.linesize = s->linesize;
-	rq.width = s->width;
-	rq.height = s->height;
+	rq.width = sw;
+	rq.height = sh;
+	rq.scale_x = scale;
+	rq.scale_y = rows_prescaled ? 1u : scale;
+	rq.strict = !surface && pr->xform == SCOPE_XFORM_FP32_STRICT;
 	rq.n_frames = n_frames;
 	rq.frame_stride = frame_stride;
 	rq.colorspace = s->colorspace;
@@ -522,13 +547,33 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	rq.hist = hist;
 	rq.hist_stride = hist_stride;
 	rq.wave = out->wave;
-	rq.wave_stride = scope_wave_bytes(s->width);
+	rq.wave_stride = scope_wave_bytes(sw);
 	rq.wave_pairs = nullptr;
 	rq.x_offset = 0;
-	rq.out_width = s->width;
+	rq.out_width = sw;
 	rq.partial = 0;
 	rq.vs_acc = vs_acc;
 	rq.vs_stride = 65536;
+
+	// the reference's named profile scopes (histogram.c:10-19, waveform.c:8-18, vectorscope.c:10-20), as NVTX
+	// ranges around the launches that do their work; one fused launch carries all the names it serves
+	struct ScopeRanges {
+		int n = 0;
+		ScopeRanges(bool h, bool w, bool v)
+		{
+			if (h)
+				nvtxRangePushA("draw_histogram"), n++;
+			if (w)
+				nvtxRangePushA("draw_waveform"), n++;
+			if (v)
+				nvtxRangePushA("draw_vectorscope"), n++;
+		}
+		~ScopeRanges()
+		{
+			while (n-- > 0)
+				nvtxRangePop();
+		}
+	} ranges(want_hist, want_wave, want_vs);
 
 	// One launch when histogram and waveform read the same plane (or only one of them is
 	// on); otherwise the histogram gets its own launch with the vectorscope riding on the
@@ -577,13 +622,13 @@ int run_device(scope_ctx *ctx, const scope_params *pr, const scope_surface *s, u
 	// and hi_max keeps its previous contents - so nothing is written here either)
 	if (want_hist && out->hist_max && (pr->hist_components & 0x77u)) {
 		hist_max_kernel<<<n_frames, 256, 0, stream>>>(hist, hist_stride, out->hist_max, pr->hist_components,
-							       s->width, s->height, pr->level_fixed_value,
+							       sw, sh, pr->level_fixed_value,
 							       pr->level_ratio_value);
 		CU_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}
 	if (want_wave && out->wave_display && pr->wave_intensity > 0) {
-		const size_t words = (size_t)n_frames * scope_wave_bytes(s->width) / 4;
+		const size_t words = (size_t)n_frames * scope_wave_bytes(sw) / 4;
 		wave_display_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(out->wave, out->wave_display, words,
 										       (float)pr->wave_intensity);
 		CU_TRY(ctx, cudaGetLastError());
@@ -691,24 +736,34 @@ int submit_host(scope_ctx *ctx, int slot, const scope_params *pr, const scope_su
 	if ((need_rgb && !s->rgb_data) || (need_yuv && !s->yuv_data))
 		return fail(ctx, SCOPE_ERR_INVALID, "a plane the request needs is NULL");
 
-	// device copy: rows packed at a 16-byte-multiple pitch so the TMA path applies
+	// device copy: rows packed at a 16-byte-multiple pitch so the TMA path applies.  With target_scale only every
+	// scale-th row is needed (row y of the scaled surface = source row y s + s / 2): the copy takes just those, so
+	// the bus carries 1 / s of the frame; the columns are picked by the kernel
+	const uint32_t scale = pr->target_scale > 1 ? pr->target_scale : 1u;
+	if (scale > 128u || s->width / scale == 0 || s->height / scale == 0)
+		return fail(ctx, SCOPE_ERR_INVALID, "target_scale out of range for this surface");
+	const uint32_t rows = s->height / scale, out_w = s->width / scale;
+	const size_t row0 = (size_t)(scale / 2u) * s->linesize, src_pitch = (size_t)s->linesize * scale;
 	const uint32_t pitch = (s->width * 4u + 15u) & ~15u;
-	const size_t plane_bytes = (size_t)pitch * s->height;
-	int r = ensure_slot(ctx, sl, plane_bytes * 2, s->width);
+	const size_t plane_bytes = (size_t)pitch * rows;
+	int r = ensure_slot(ctx, sl, plane_bytes * 2, out_w);
 	if (r)
 		return r;
 	uint8_t *d_rgb = sl.d_in, *d_yuv = sl.d_in + plane_bytes;
+	nvtxRangePushA("stage_surface"); // common.c:316-320: the copy of the frame towards the consumer
 	if (need_rgb)
-		CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb, pitch, s->rgb_data, s->linesize, (size_t)s->width * 4, s->height,
+		CU_TRY(ctx, cudaMemcpy2DAsync(d_rgb, pitch, s->rgb_data + row0, src_pitch, (size_t)s->width * 4, rows,
 					      cudaMemcpyHostToDevice, sl.stream));
 	if (need_yuv)
-		CU_TRY(ctx, cudaMemcpy2DAsync(d_yuv, pitch, s->yuv_data, s->linesize, (size_t)s->width * 4, s->height,
+		CU_TRY(ctx, cudaMemcpy2DAsync(d_yuv, pitch, s->yuv_data + row0, src_pitch, (size_t)s->width * 4, rows,
 					      cudaMemcpyHostToDevice, sl.stream));
+	nvtxRangePop();
 
 	scope_surface ds = *s;
 	ds.rgb_data = need_rgb ? d_rgb : nullptr;
 	ds.yuv_data = need_yuv ? d_yuv : nullptr;
 	ds.linesize = pitch;
+	ds.height = rows; // (rows already dropped; run_device scales the width only)
 	scope_out_device od{};
 	od.hist_counts = sl.d_hist;
 	od.hist_max = sl.d_hist_max;
@@ -716,12 +771,12 @@ int submit_host(scope_ctx *ctx, int slot, const scope_params *pr, const scope_su
 	od.wave_display = pr->wave_intensity > 0 ? sl.d_wave_disp : nullptr;
 	od.vscope = sl.d_vscope;
 	od.vscope_display = pr->vscope_intensity > 0 ? sl.d_vscope_disp : nullptr;
-	r = run_device(ctx, pr, &ds, 1, plane_bytes, &od, sl.stream, sl.d_vs_acc);
+	r = run_device(ctx, pr, &ds, 1, plane_bytes, &od, sl.stream, sl.d_vs_acc, /*rows_prescaled=*/true);
 	if (r)
 		return r;
 
 	// results -> pinned staging
-	const size_t wb = scope_wave_bytes(s->width);
+	const size_t wb = scope_wave_bytes(out_w);
 	uint8_t *h = sl.h_res;
 	if (hist_on) {
 		CU_TRY(ctx, cudaMemcpyAsync(h, sl.d_hist, 4096, cudaMemcpyDeviceToHost, sl.stream));
@@ -741,8 +796,8 @@ int submit_host(scope_ctx *ctx, int slot, const scope_params *pr, const scope_su
 	}
 	CU_TRY(ctx, cudaEventRecord(sl.done, sl.stream));
 	sl.params = *pr;
-	sl.width = s->width;
-	sl.height = s->height;
+	sl.width = out_w;
+	sl.height = rows;
 	sl.in_flight = true;
 	return SCOPE_OK;
 }
@@ -1018,6 +1073,8 @@ int accumulate_band(scope_ctx *ctx, const struct scope_params *pr, const struct 
 		return fail(ctx, SCOPE_ERR_INVALID, "bad tile geometry");
 	if (wave_outs && (n_wave_outs == 0 || n_wave_outs > (uint32_t)kMaxWaveCopies + 1u))
 		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "scope_accumulate_band: 1..16 waveform outputs");
+	if (pr->target_scale > 1)
+		return fail(ctx, SCOPE_ERR_UNSUPPORTED, "tile-sharded frames take the scaled surface (target_scale <= 1 here)");
 	const bool surface = pr->mode == SCOPE_MODE_SURFACE;
 	const bool want_hist = (pr->scopes & SCOPE_HIST) && partial && partial->hist_counts;
 	const bool want_wave = (pr->scopes & SCOPE_WAVE) && (wave_outs ? wave_outs[0] != nullptr : (partial && partial->wave_pairs));
@@ -1038,6 +1095,7 @@ int accumulate_band(scope_ctx *ctx, const struct scope_params *pr, const struct 
 	rq.frame_stride = 0;
 	rq.colorspace = tile->colorspace;
 	rq.surface = surface;
+	rq.strict = !surface && pr->xform == SCOPE_XFORM_FP32_STRICT;
 	rq.hist = partial ? partial->hist_counts : nullptr;
 	rq.hist_stride = 1024;
 	rq.x_offset = x_offset;
@@ -1345,6 +1403,19 @@ int scope_debug_yuv_table(scope_ctx *ctx, int colorspace, uint32_t *d_out /* dev
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	DeviceGuard guard(ctx->device);
 	yuv_table_kernel<<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(coef_for(colorspace), d_out);
+	CU_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return SCOPE_OK;
+}
+
+// test hook: SCOPE_XFORM_FP32_STRICT over all 2^24 colours, d_out[r<<16|g<<8|b] = u | y<<8 | v<<16
+int scope_debug_yuv_table_strict(scope_ctx *ctx, int colorspace, uint32_t *d_out /* device, 1<<24 u32 */, void *stream)
+{
+	if (!ctx || !d_out)
+		return SCOPE_ERR_INVALID;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	DeviceGuard guard(ctx->device);
+	yuv_table_strict_kernel<<<(1u << 24) / 512, 256, 0, (cudaStream_t)stream>>>(colorspace, d_out);
 	CU_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
 	return SCOPE_OK;

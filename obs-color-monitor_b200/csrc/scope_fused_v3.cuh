@@ -730,7 +730,13 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 	for (;;) {
 		// the chunk id becomes readable once the chunk's first tile (or the end marker) lands in stage 0
 		mbar_wait(bar_full, ph.ph[0]);
-		const uint32_t first = chunk_q[2 * (qr % kQueue)], count = chunk_q[2 * (qr % kQueue) + 1];
+		uint32_t first = 0, count = 0;
+		if (lane == 0) { // (the lane that hands stages back reads the mailbox for the warp, see tma_consume)
+			first = chunk_q[2 * (qr % kQueue)];
+			count = chunk_q[2 * (qr % kQueue) + 1];
+		}
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		count = __shfl_sync(0xFFFFFFFFu, count, 0);
 		qr++;
 		if (count == 0u)
 			break;

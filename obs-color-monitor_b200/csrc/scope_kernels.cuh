@@ -215,6 +215,13 @@ struct StripParams {
 	uint32_t *vscope_acc;     // [n][65536] u32, zeroed
 	unsigned long long hist_stride, wave_stride, vscope_stride; // elements between frames
 	uint8_t *wave_copies[kMaxWaveCopies]; // column-band sharding: every rank's image gets this rank's columns
+	uint32_t scale_x, scale_y; // plain-load kernel: point-downsample (0 or 1: none): pixel (x, y) of the pass is the source
+	                          // pixel (x * scale_x + scale_x / 2, y * scale_y + scale_y / 2); width / height are the
+	                          // SCALED size (target size / target_scale, common.c:249-250).  The host entry points
+	                          // drop the rows while copying (scale_y = 1 on the device then)
+	uint32_t xform_strict;    // plain-load kernel, fused mode: evaluate the transform in fp32, every product and sum
+	                          // rounded separately (SCOPE_XFORM_FP32_STRICT) instead of the exact integer form
+	int32_t colorspace;       // 1 = BT.601, else BT.709 (only the strict transform looks at it; the exact one has `coef`)
 	uint32_t rt_zero;         // always 0, but only known at run time: the consumers AND it with the pixels they loaded
 	                          // and add it to the address of the "stage is free" arrive, so that ptxas must keep the
 	                          // arrive behind the arrival of the data (a `mov 0` inside inline PTX is folded by ptxas)
@@ -530,6 +537,42 @@ __device__ __forceinline__ void rgb_to_yuv_carriers(const uint32_t (&bgr)[3], co
 	yuv[2] = carrier<2>(hi[2], magic);
 }
 
+// SCOPE_XFORM_FP32_STRICT: the fp32 reading of data/common.effect:23-43 that SURVEY.md 8(c) drafted and
+// oracle/scope_oracle.c keeps as variant 1 ("strict"): xf = (float)X / 255.0f, every product and sum rounded
+// separately, left to right, no FMA; q = floor(min(max(t, 0), 1) * 255 + 0.5) with the product and the sum
+// rounded separately as well.  It differs from the exact value on 0-387 of the 2^24 colours per channel, by one
+// step.  pixel = the BGRA word; result bytes U, Y, V as plain integers.
+#ifndef SCOPE_EMULATE
+__device__ __forceinline__ uint32_t strict_channel(float r, float g, float b, float c0, float c1, float c2, float off)
+{
+	float s = __fadd_rn(__fmul_rn(c0, r), __fmul_rn(c1, g));
+	s = __fadd_rn(s, __fmul_rn(c2, b));
+	s = __fadd_rn(s, off);
+	s = fminf(fmaxf(s, 0.0f), 1.0f);
+	return (uint32_t)floorf(__fadd_rn(__fmul_rn(s, 255.0f), 0.5f));
+}
+__device__ __forceinline__ void rgb_to_yuv_strict(uint32_t pixel, int colorspace, uint32_t (&uyv)[3])
+{
+	const float b = __fdiv_rn((float)(pixel & 0xFFu), 255.0f), g = __fdiv_rn((float)((pixel >> 8) & 0xFFu), 255.0f),
+		    r = __fdiv_rn((float)((pixel >> 16) & 0xFFu), 255.0f);
+	const float off_u = 0.5f - 1.0f / 256.0f;
+	if (colorspace == 1) {
+		uyv[0] = strict_channel(r, g, b, -0.147643f, -0.289855f, +0.437500f, off_u);
+		uyv[1] = strict_channel(r, g, b, +0.299000f, +0.587000f, +0.114000f, 0.0f);
+		uyv[2] = strict_channel(r, g, b, +0.437500f, -0.366351f, -0.071147f, 0.5f);
+	} else {
+		uyv[0] = strict_channel(r, g, b, -0.100643f, -0.338571f, +0.439216f, off_u);
+		uyv[1] = strict_channel(r, g, b, +0.212600f, +0.715200f, +0.072200f, 0.0f);
+		uyv[2] = strict_channel(r, g, b, +0.439216f, -0.398941f, -0.040273f, 0.5f);
+	}
+}
+#else
+__device__ __forceinline__ void rgb_to_yuv_strict(uint32_t, int, uint32_t (&uyv)[3]) // (the emulator runs the exact form only)
+{
+	uyv[0] = uyv[1] = uyv[2] = 0;
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // shared-memory layout
 // ---------------------------------------------------------------------------
@@ -694,6 +737,8 @@ __device__ __forceinline__ void vs_undo(const VsAdd &a)
 struct TileCtx {
 	uint32_t vs_base, wb0, wb1, magic, bins_mask;
 	int lane;
+	uint32_t strict = 0; // SCOPE_XFORM_FP32_STRICT (plain-load kernel only)
+	int colorspace = 2;
 };
 
 template <int SRC, bool VSCOPE, bool SURFACE, bool FAST, int N>
@@ -712,9 +757,20 @@ __device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef,
 		}
 	}
 	if (kTransform) {
+		if (c.strict) {
 #pragma unroll
-		for (int k = 0; k < N; k++)
-			rgb_to_yuv_carriers<SRC == SRC_YUV>(crgb[k], coef, c.magic, cyuv[k]);
+			for (int k = 0; k < N; k++) {
+				uint32_t uyv[3];
+				rgb_to_yuv_strict(p[k], c.colorspace, uyv);
+#pragma unroll
+				for (int j = 0; j < 3; j++)
+					cyuv[k][j] = uyv[j] + kCarrierBias;
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < N; k++)
+				rgb_to_yuv_carriers<SRC == SRC_YUV>(crgb[k], coef, c.magic, cyuv[k]);
+		}
 	} else if (SURFACE && SRC == SRC_YUV) {
 #pragma unroll
 		for (int k = 0; k < N; k++) {
@@ -1333,7 +1389,16 @@ __device__ __forceinline__ void tma_consume(const StripParams &P, uint8_t *smem,
 	for (;;) {
 		// the chunk id becomes readable once the chunk's first tile (or the end marker) lands
 		mbar_wait(bar_full + 8 * stage, phase);
-		const uint32_t first = chunk_q[2 * (qr % kQueue)], count = chunk_q[2 * (qr % kQueue) + 1];
+		// (lane 0 reads the mailbox for the warp: it is also the lane whose arrive hands stages back, so the
+		// read is ordered before the producer's next write of this entry by one thread's program order -
+		// which is also all that compute-sanitizer's racecheck can follow)
+		uint32_t first = 0, count = 0;
+		if (lane == 0) {
+			first = chunk_q[2 * (qr % kQueue)];
+			count = chunk_q[2 * (qr % kQueue) + 1];
+		}
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		count = __shfl_sync(0xFFFFFFFFu, count, 0);
 		qr++;
 		if (count == 0u)
 			break;
@@ -1632,9 +1697,12 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 	uint32_t magic;
 	magic = opaque_carrier_bias();
 	const TileCtx tc{smem_base + L::kVsOff, wave_lane_addr - kCarrierBias * 128u,
-			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane};
+			 wave_lane_addr - kCarrierBias * 128u + kWaveWords * 4, magic, P.bins_mask, lane,
+			 P.xform_strict, P.colorspace};
 	const Coef coef = P.coef;
 	uint32_t cur_frame = 0xFFFFFFFFu;
+	// target_scale: this pass's pixel (x, y) is the source pixel (x s + s / 2, y s + s / 2)
+	const uint32_t scx = P.scale_x ? P.scale_x : 1u, scy = P.scale_y ? P.scale_y : 1u;
 
 	for (uint32_t item = first; item < last; item++) {
 		const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
@@ -1644,7 +1712,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 		const uint32_t x = strip * kStripPx + lane;
 		const bool lane_ok = x < P.width;
 		const bool strip_full = strip * kStripPx + kStripPx <= P.width;
-		const size_t col = (size_t)frame * P.frame_stride + (size_t)(lane_ok ? x : 0) * 4;
+		const size_t col = (size_t)frame * P.frame_stride + ((size_t)(lane_ok ? x : 0) * scx + scx / 2u) * 4;
 
 		for (uint32_t g = warp; g < groups; g += NW) {
 			const uint32_t y0 = g * RPW;
@@ -1657,7 +1725,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 1) scope_strip_kernel_ldg(cons
 				p[k] = 0;
 				q[k] = 0;
 				if (ok[k]) {
-					const size_t o = col + (size_t)(y0 + k) * P.linesize;
+					const size_t o = col + ((size_t)(y0 + k) * scy + scy / 2u) * P.linesize;
 					if (L::kLoadRgb)
 						p[k] = ld_nc_u32(P.rgb + o);
 					if (L::kLoadYuv)
@@ -1767,6 +1835,17 @@ __global__ void __launch_bounds__(256) wave_pairs_finalize_kernel(const uint32_t
 }
 
 // test hook: the kernel's own transform for all 2^24 colours (index r<<16|g<<8|b)
+__global__ void __launch_bounds__(256) yuv_table_strict_kernel(int colorspace, uint32_t *out)
+{
+	const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 2;
+#pragma unroll
+	for (uint32_t j = i; j < i + 2; j++) {
+		uint32_t uyv[3];
+		rgb_to_yuv_strict(j, colorspace, uyv);
+		out[j] = uyv[0] | (uyv[1] << 8) | (uyv[2] << 16);
+	}
+}
+
 __global__ void __launch_bounds__(256) yuv_table_kernel(Coef coef, uint32_t *out)
 {
 	const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 2;

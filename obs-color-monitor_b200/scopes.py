@@ -39,6 +39,8 @@ class ScopeSettings:
     logscale: bool = False
     wave_intensity: int = 0           # 0 = no display image; reference default 51 (waveform.c:114)
     vscope_intensity: int = 0         # reference default 25 (vectorscope.c:158)
+    target_scale: int = 1             # point-downsample first (common.c:88-90,249-250); the reference's default is 2
+    xform: int = 0                    # 0 = exact transform, 1 = SCOPE_XFORM_FP32_STRICT
 
     def to_c(self) -> Params:
         p = Params()
@@ -51,6 +53,8 @@ class ScopeSettings:
         p.logscale = int(self.logscale)
         p.wave_intensity = self.wave_intensity
         p.vscope_intensity = self.vscope_intensity
+        p.target_scale = self.target_scale
+        p.xform = self.xform
         return p
 
 
@@ -123,7 +127,7 @@ class ScopeEngine:
         """Synchronous: one mapped surface in, the scopes' buffers out (numpy)."""
         st = settings or ScopeSettings()
         s = self._host_surface(rgb, yuv, width, st)
-        res, out = self._host_out(st, s.width)
+        res, out = self._host_out(st, s.width // max(1, st.target_scale))
         p = st.to_c()
         self.ctx.check(self.lib.scope_accumulate_host(self.ctx.handle, C.byref(p), C.byref(s), C.byref(out)))
         return res
@@ -139,7 +143,7 @@ class ScopeEngine:
             return False
         self.ctx.check(rc)
         self._pending = getattr(self, "_pending", {})
-        self._pending[slot] = (st, s.width)
+        self._pending[slot] = (st, s.width // max(1, st.target_scale))
         return True
 
     def wait_host(self, slot: int):
@@ -195,7 +199,7 @@ class ScopeEngine:
         s.yuv_data = yuv.data_ptr() if yuv is not None else None
         s.linesize, s.width, s.height, s.colorspace = linesize, width, h, st.colorspace
         if out is None:
-            out = self.alloc_device_out(n, width, st, ref.device)
+            out = self.alloc_device_out(n, width // max(1, st.target_scale), st, ref.device)
         od = OutDevice()
         od.hist_counts = out["hist"].data_ptr() if "hist" in out else None
         od.hist_max = out["hist_max"].data_ptr() if "hist_max" in out else None
@@ -393,6 +397,15 @@ class ScopeEngine:
                                                          C.byref(pd), slice_index, slice_count, C.byref(lo),
                                                          C.byref(mi) if mi is not None else None, C.c_void_p(stream)))
         return local_out
+
+    def debug_yuv_table_strict(self, colorspace: int):
+        """test hook: SCOPE_XFORM_FP32_STRICT for all 2^24 colours, u | y<<8 | v<<16"""
+        import torch
+
+        out = torch.empty(1 << 24, dtype=torch.int32, device="cuda")
+        self.ctx.check(self.lib.scope_debug_yuv_table_strict(self.ctx.handle, colorspace, out.data_ptr(),
+                                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
 
     def debug_uv_table_v3(self, colorspace: int):
         """test hook: U | V << 8 of the headline kernel's own transform for all 2^24 colours"""

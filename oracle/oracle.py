@@ -103,6 +103,26 @@ class Oracle:
         self.lib.orc_rgb_to_yuv(_ptr(bgra), ls, w, h, colorspace, out.ctypes.data, w * 4)
         return out
 
+    def downsample(self, plane: np.ndarray, scale: int, width: Optional[int] = None) -> np.ndarray:
+        """target_scale: (H, W, 4) -> (H // scale, W // scale, 4), point-sampled at the texel centres
+        (orc_point_downsample; src/common.c:249-250)"""
+        ls, w, h = _plane_geometry(plane, width, None)
+        s = max(1, int(scale))
+        out = np.zeros((h // s, w // s, 4), np.uint8)
+        self.lib.orc_point_downsample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p, C.c_uint32]
+        self.lib.orc_point_downsample.restype = None
+        self.lib.orc_point_downsample(_ptr(plane), ls, w, h, s, out.ctypes.data, (w // s) * 4)
+        return out
+
+    def yuv_from_table(self, bgra: np.ndarray, table: np.ndarray) -> np.ndarray:
+        """[U, Y, V, 255] plane of a frame through one of rgb_to_yuv_table's 2^24-entry tables"""
+        idx = (bgra[..., 2].astype(np.uint32) << 16) | (bgra[..., 1].astype(np.uint32) << 8) | bgra[..., 0]
+        t = table[idx]
+        out = np.empty(bgra.shape, np.uint8)
+        out[..., 0], out[..., 1], out[..., 2], out[..., 3] = t & 0xFF, (t >> 8) & 0xFF, (t >> 16) & 0xFF, 255
+        return out
+
     TRANSFORM_VARIANTS = {"exact": 0, "fp32_strict": 1, "fp32_contracted": 2}
 
     def rgb_to_yuv_table(self, colorspace: int, variant: str = "exact") -> Tuple[np.ndarray, bool]:

@@ -224,6 +224,26 @@ ORC_API int orc_rgb_to_yuv_table(int colorspace, int variant, uint32_t *out /* 1
 	return out_of_range;
 }
 
+/* target_scale (src/common.c:88-90: 1..128; :249-250: the scopes' surface is target size / target_scale, integer
+ * division).  In the reference the target is DRAWN into the smaller texrender (render_target_to_texrender,
+ * common.c:141-168: gs_ortho over the full target size), so how a texel is filled belongs to the target's own
+ * sampler; the rule pinned here is point sampling: texel (x, y) takes the source pixel that contains the texel's
+ * centre, ((x + 1/2) s, (y + 1/2) s) -> (x s + s / 2, y s + s / 2) (for even s the centre lies on a pixel corner
+ * and the top-left fill rule selects the pixel to its lower right).  dst is (width / s) x (height / s). */
+ORC_API void orc_point_downsample(const uint8_t *src, uint32_t linesize, uint32_t width, uint32_t height,
+				  uint32_t scale, uint8_t *dst, uint32_t dst_linesize)
+{
+	if (scale == 0)
+		scale = 1;
+	const uint32_t w = width / scale, h = height / scale;
+	for (uint32_t y = 0; y < h; y++) {
+		const uint8_t *row = src + (size_t)linesize * (y * scale + scale / 2);
+		uint8_t *d = dst + (size_t)dst_linesize * y;
+		for (uint32_t x = 0; x < w; x++)
+			memcpy(d + 4 * x, row + 4 * (size_t)(x * scale + scale / 2), 4);
+	}
+}
+
 /* src/util.c:25-41 with the OBS video-info lookup replaced by its default */
 ORC_API int orc_calc_colorspace(int colorspace)
 {

@@ -266,3 +266,64 @@ def test_surface_mode_matches_reference_golden(engine, pkg, case):
                                       g[f"{case}/hist/{comp:02x}/{key}"].view(np.uint32)), (case, hex(comp), key)
         assert np.array_equal(res["wave"], g[f"{case}/wave/{comp:02x}"]), (case, hex(comp))
         assert np.array_equal(res["vscope"], g[f"{case}/vscope"]), case
+
+
+def test_transform_exhaustive_fp32_strict(engine, oracle):
+    """SCOPE_XFORM_FP32_STRICT (SURVEY.md 8(c)'s fp32 reading of data/common.effect:23-43: every product and sum
+    rounded separately, no FMA) for all 2^24 colours == the oracle's "fp32_strict" table"""
+    for cs in (1, 2):
+        exp, _ = oracle.rgb_to_yuv_table(cs, "fp32_strict")
+        got = engine.debug_yuv_table_strict(cs).cpu().numpy().view(np.uint32)
+        bad = np.nonzero(got != exp)[0]
+        assert bad.size == 0, f"colorspace {cs}: {bad.size} colours differ, first {bad[:5]}"
+
+
+def test_fp32_strict_mode_scopes(engine, oracle, pkg):
+    """xform = SCOPE_XFORM_FP32_STRICT through the host and the device entry points: every scope equals the oracle's
+    loops run on the YUV plane the strict table gives (fused mode; YUV components so that the transform feeds all
+    three scopes).  The frame holds colours on which strict and exact differ, so the mode is really selected."""
+    import torch
+    exact, _ = oracle.rgb_to_yuv_table(2, "exact")
+    strict, _ = oracle.rgb_to_yuv_table(2, "fp32_strict")
+    diff = np.nonzero(exact != strict)[0][:4000]
+    assert diff.size > 100
+    f = pkg.frames.natural(200, 120, seed=5)
+    flat = f.reshape(-1, 4)
+    flat[: diff.size, 0], flat[: diff.size, 1], flat[: diff.size, 2] = diff & 0xFF, (diff >> 8) & 0xFF, diff >> 16
+    yuv = oracle.yuv_from_table(f, strict)
+    assert not np.array_equal(yuv, oracle.rgb_to_yuv(f, 2))
+    for comps in ((0x70, 0x70), (0x07, 0x07)):
+        st = pkg.ScopeSettings(hist_components=comps[0], wave_components=comps[1], xform=1, vscope_intensity=25)
+        res = engine.accumulate_host(f, settings=st)
+        _check(res, oracle, f, yuv, st, f"strict host {comps}")
+        out = engine.accumulate_device(torch.from_numpy(f[None]).cuda(), settings=st)
+        assert np.array_equal(out["vscope"][0].cpu().numpy(), oracle.vectorscope(yuv))
+        assert np.array_equal(out["wave"][0].cpu().numpy(), oracle.waveform(comps[1], f, yuv))
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4, 7])
+def test_target_scale(engine, oracle, pkg, scale):
+    """scope_params.target_scale (common.c:88-90,249-250): the scopes of the point-downsampled surface, host entry
+    point (rows dropped by the copy), ring and device entry point (rows and columns picked by the kernel)"""
+    import torch
+    w, h = 333, 207                       # neither a multiple of the scale
+    f = pkg.frames.natural(w, h, seed=scale)
+    f[::5, ::3, 3] = 0                    # some transparent pixels
+    small = oracle.downsample(f, scale)
+    assert small.shape == (h // scale, w // scale, 4)
+    yuv = oracle.rgb_to_yuv(small, 2)
+    st = pkg.ScopeSettings(target_scale=scale, vscope_intensity=25, wave_intensity=51, level_ratio_value=500)
+    res = engine.accumulate_host(f, settings=st)
+    _check(res, oracle, small, yuv, st, f"scale {scale} host")
+    assert engine.submit_host(1, f, settings=st) is True
+    _check(engine.wait_host(1), oracle, small, yuv, st, f"scale {scale} ring")
+    out = engine.accumulate_device(torch.from_numpy(np.stack([f, f])).cuda(), settings=st)
+    for i in range(2):
+        assert np.array_equal(out["hist"][i].cpu().numpy().view(np.uint32), oracle.histogram_counts(7, small, yuv).ravel())
+        assert np.array_equal(out["wave"][i].cpu().numpy(), oracle.waveform(7, small, yuv))
+        assert np.array_equal(out["vscope"][i].cpu().numpy(), oracle.vectorscope(yuv))
+    # strict drop-in mode: both planes scaled the same way
+    full_yuv = oracle.rgb_to_yuv(f, 2)
+    st2 = pkg.ScopeSettings(mode=pkg.MODE_SURFACE, target_scale=scale, hist_components=0x70, wave_components=0x20)
+    res = engine.accumulate_host(f, full_yuv, settings=st2)
+    _check(res, oracle, small, oracle.downsample(full_yuv, scale), st2, f"scale {scale} surface mode")

@@ -4,46 +4,29 @@ import ctypes as C
 import threading
 import time
 
+import os
+import sys
+
 import numpy as np
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from obs_color_monitor_b200 import shim as S  # noqa: E402  (ctypes mirror of include/cm_shim.h, sizes checked at load)
 
-class SurfaceData(C.Structure):
-    _fields_ = [("rgb_data", C.c_void_p), ("yuv_data", C.c_void_p), ("linesize", C.c_uint32),
-                ("width", C.c_uint32), ("height", C.c_uint32), ("colorspace", C.c_int), ("tex", C.c_void_p)]
-
-
-CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(SurfaceData))
+SurfaceData, CB = S.SurfaceData, S.SURFACE_CB
+_His, _Wvs, _Vss, _Cm = S.HisSource, S.WvsSource, S.VssSource, S.CmSource
 
 
 @pytest.fixture()
 def shim(pkg):
-    lib = C.CDLL(pkg._ffi.SHIM_PATH)
-    lib.b200_cm_render_target.restype = C.c_bool
-    lib.b200_cm_render_target.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib = S.load()
     lib.b200_cm_request.argtypes = [C.c_void_p, CB, C.c_void_p]
-    for n in ("b200_cm_create", "b200_cm_destroy", "b200_cm_tick", "b200_cm_drain"):
-        getattr(lib, n).argtypes = [C.c_void_p]
     return lib
 
 
 def test_ring_orders_frames_and_drops_when_busy(shim, pkg):
     lib = shim
-    # compile-time layout probe: a tiny C helper is overkill; use offsetof via ctypes mirror
-    class Item(C.Structure):
-        _fields_ = [("staged", C.c_void_p), ("staged_bytes", C.c_size_t), ("width", C.c_uint32),
-                    ("height", C.c_uint32), ("linesize", C.c_uint32), ("flags", C.c_uint32),
-                    ("colorspace", C.c_int), ("cb", C.c_void_p), ("cb_data", C.c_void_p)]
-
-    class Cm(C.Structure):
-        _fields_ = [("queue", Item * 3), ("i_write_queue", C.c_int), ("i_staging_queue", C.c_int),
-                    ("i_read_queue", C.c_int), ("rendered", C.c_bool), ("pipeline_thread", C.c_ulong),
-                    ("pipeline_mutex", C.c_byte * 40), ("pipeline_cond", C.c_byte * 48),
-                    ("pipeline_thread_running", C.c_bool), ("request_exit", C.c_bool), ("worker_busy", C.c_bool),
-                    ("callback", C.c_void_p), ("callback_data", C.c_void_p), ("flags", C.c_uint32),
-                    ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong),
-                    ("x0", C.c_int), ("x1", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
-
+    Cm = S.CmSource
     cm = Cm()
     lib.b200_cm_create(C.byref(cm))
     assert (cm.i_write_queue, cm.i_staging_queue, cm.i_read_queue) == (0, 0, 2)
@@ -105,38 +88,25 @@ def test_ring_orders_frames_and_drops_when_busy(shim, pkg):
 def test_roi_interleave_pacing(shim, pkg):
     """n_interleave = 1 (the reference default): frames are staged on every other tick only."""
     lib = shim
-    lib.b200_roi_target_render.restype = C.c_bool
-    lib.b200_roi_target_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
-                                           C.c_uint32]
-    lib.b200_roi_tick.argtypes = [C.c_void_p, C.c_void_p]
-    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-
-    class Roi(C.Structure):
-        _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("sources_mutex", C.c_byte * 40),
-                    ("his", C.c_void_p * 8), ("wvs", C.c_void_p * 8), ("vss", C.c_void_p * 8),
-                    ("n_his", C.c_int), ("n_wvs", C.c_int), ("n_vss", C.c_int), ("wave_tmp", C.c_void_p),
-                    ("wave_tmp_width", C.c_uint32), ("n_interleave", C.c_int), ("i_interleave", C.c_int),
-                    ("interleave_rendered", C.c_bool)]
-
+    Roi = S.RoiSource
     roi = Roi()
     lib.b200_roi_init(C.byref(roi), None, 1)
-    cm = C.create_string_buffer(4096)
+    cm_obj = S.CmSource()
+    cm = C.byref(cm_obj)
     lib.b200_cm_create(cm)
-    # flags = CONVERT_RGB: locate the field through the documented layout of the first test
-    flags_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16
     seen = []
     cfn = CB(lambda _d, sd: seen.append(int(C.cast(sd.contents.rgb_data, C.POINTER(C.c_uint8))[0])))
     lib.b200_cm_request(cm, cfn, None)
-    C.c_uint32.from_buffer(cm, flags_off).value = 1
+    cm_obj.flags = 1            # CONVERT_RGB
     staged = []
     for interleave in (1, 0):
         roi.n_interleave, roi.i_interleave, roi.interleave_rendered = interleave, 0, False
         for tick in range(8):
             lib.b200_roi_tick(C.byref(roi), cm)
             f = np.full((4, 64), 10 * interleave + tick, np.uint8)
-            before = C.c_int.from_buffer(cm, 3 * 56).value          # i_write_queue
+            before = cm_obj.i_write_queue
             lib.b200_roi_target_render(C.byref(roi), cm, f.ctypes.data, None, 64, 16, 4)
-            staged.append((interleave, tick, C.c_int.from_buffer(cm, 3 * 56).value != before))
+            staged.append((interleave, tick, cm_obj.i_write_queue != before))
             lib.b200_cm_drain(cm)
     on = [t for i, t, s in staged if i == 1 and s]
     assert on == [0, 2, 4, 6]                                        # every other tick
@@ -148,18 +118,17 @@ def test_roi_crop_is_staged_like_the_reference(shim, pkg):
     """B200_CM_FLAG_ROI: the capture core stages only the ROI rectangle (common.c:272-291), clamped
     like roi_send_range (roi.c:478-500); the callback sees a cx x cy surface, RGB rows then YUV rows."""
     lib = shim
-    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
     W, H = 40, 24
     rng = np.random.default_rng(5)
     rgb = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
     yuv = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
-    flags_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16
     cases = [((5, 3, 17, 20), (5, 3, 17, 20)),        # inside
              ((-4, -1, 100, 9), (0, 0, W, 9)),        # negative / too large ends snap to the border
              ((7, 2, -1, -1), (7, 2, W, H)),          # -1 = "to the end"
              ((9, 9, 9, 12), None)]                   # empty rectangle: whole frame (common.c:273 fails)
     for (x0, y0, x1, y1), want in cases:
-        cm = C.create_string_buffer(4096)
+        cm_obj = S.CmSource()
+        cm = C.byref(cm_obj)
         lib.b200_cm_create(cm)
         got = []
 
@@ -172,9 +141,9 @@ def test_roi_crop_is_staged_like_the_reference(shim, pkg):
 
         cfn = CB(cb)
         lib.b200_cm_request(cm, cfn, None)
-        C.c_uint32.from_buffer(cm, flags_off).value = 3   # CONVERT_RGB | CONVERT_YUV
+        cm_obj.flags = 3   # CONVERT_RGB | CONVERT_YUV
         lib.b200_cm_set_roi(cm, x0, y0, x1, y1, W, H)
-        assert C.c_uint32.from_buffer(cm, flags_off).value == 3 | 8
+        assert cm_obj.flags == 3 | 8
         for _ in range(2):                                # one-frame staging latency: render twice
             lib.b200_cm_tick(cm)
             lib.b200_cm_render_target(cm, rgb.ctypes.data, yuv.ctypes.data, W * 4, W, H)
@@ -195,12 +164,6 @@ def test_callback_early_returns_match_the_reference(shim, ref):
     (oracle/_ref): the reference processed a surface iff it flipped w_tex_buf.  Whole truth table:
     components incl. none / both planes' bits, each plane present or NULL, empty surfaces."""
     lib, L = shim, ref.lib
-    for n in ("b200_his_inputs_missing", "b200_wvs_inputs_missing", "b200_vss_inputs_missing"):
-        getattr(lib, n).restype = C.c_bool
-        getattr(lib, n).argtypes = [C.c_void_p, C.POINTER(SurfaceData)]
-    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
     rgb = np.full((3, 16), 200, np.uint8)
     yuv = np.full((3, 16), 90, np.uint8)
     scratch = np.zeros(256 * 16 * 4 + 65536, np.uint8)
@@ -234,39 +197,12 @@ def test_callback_early_returns_match_the_reference(shim, ref):
     assert n_cases == 8 * 2 * 2 * 4
 
 
-class _His(C.Structure):
-    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("components", C.c_uint32), ("level_fixed_value", C.c_int),
-                ("level_ratio_value", C.c_int), ("logscale", C.c_bool), ("tex_buf", C.c_void_p * 2),
-                ("hi_max", (C.c_uint32 * 3) * 2), ("w_tex_buf", C.c_int)]
-
-
-class _Wvs(C.Structure):
-    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("components", C.c_uint32), ("tex_buf", C.c_void_p * 2),
-                ("tex_buf_width", C.c_uint32 * 2), ("w_tex_buf", C.c_int)]
-
-
-class _Vss(C.Structure):
-    _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("tex_buf", C.c_void_p * 2), ("tex_cs", C.c_int * 2),
-                ("w_tex_buf", C.c_int)]
-
-
 def test_empty_surfaces_match_the_reference(shim, ref):
     """Surfaces without rows (or without columns) never reach the GPU: the shim files the result the
     reference's loops leave when they do not iterate - zeroed buffer, level pass on zero counts, flip -
     or does nothing when the reference's callback returns early.  Compared field by field with the
     reference's own callbacks (oracle/_ref), standalone and through the ROI fan-out."""
     lib, L = shim, ref.lib
-    for n in ("b200_his_surface_cb", "b200_wvs_surface_cb", "b200_vss_surface_cb", "b200_roi_surface_cb"):
-        getattr(lib, n).argtypes = [C.c_void_p, C.POINTER(SurfaceData)]
-        getattr(lib, n).restype = None
-    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
-    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    for n in ("his", "wvs", "vss"):
-        getattr(lib, f"b200_roi_register_{n}").argtypes = [C.c_void_p, C.c_void_p]
-        getattr(lib, f"b200_{n}_destroy").argtypes = [C.c_void_p]
-    lib.b200_roi_destroy.argtypes = [C.c_void_p]
     rgb = np.full((3, 16), 200, np.uint8)
     yuv = np.full((3, 16), 90, np.uint8)
     n_flips = 0
@@ -298,7 +234,8 @@ def test_empty_surfaces_match_the_reference(shim, ref):
                         lib.b200_wvs_init(C.byref(wvs), None, comp)
                         lib.b200_vss_init(C.byref(vss), None)
                         if via_roi:
-                            roi = C.create_string_buffer(1024)
+                            roi_obj = S.RoiSource()
+                            roi = C.byref(roi_obj)
                             lib.b200_roi_init(roi, None, 1)      # SCOPE_MODE_SURFACE
                             lib.b200_roi_register_his(roi, C.byref(his))
                             lib.b200_roi_register_wvs(roi, C.byref(wvs))
@@ -343,29 +280,8 @@ def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
     L.ref_roi_add_consumer.argtypes = [C.c_void_p, C.c_uint32]
     L.ref_roi_remove_consumer.argtypes = [C.c_void_p, C.c_void_p]
     L.ref_roi_send_range.argtypes = [C.c_int] * 4 + [C.c_uint32] * 2 + [C.c_void_p]
-    lib.b200_roi_target_render.restype = C.c_bool
-    lib.b200_roi_target_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
-                                           C.c_uint32]
-    lib.b200_roi_tick.argtypes = [C.c_void_p, C.c_void_p]
-    lib.b200_roi_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_roi_destroy.argtypes = [C.c_void_p]
-    lib.b200_roi_capture_flags.restype = C.c_uint32
-    lib.b200_roi_capture_flags.argtypes = [C.c_void_p]
-    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
-    lib.b200_his_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_wvs_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-    lib.b200_vss_init.argtypes = [C.c_void_p, C.c_void_p]
-    for n in ("his", "wvs", "vss"):
-        getattr(lib, f"b200_roi_register_{n}").argtypes = [C.c_void_p, C.c_void_p]
+    Roi = S.RoiSource
 
-    class Roi(C.Structure):   # include/cm_shim.h: struct b200_roi_source
-        _fields_ = [("ctx", C.c_void_p), ("mode", C.c_uint32), ("sources_mutex", C.c_byte * 40),
-                    ("his", C.c_void_p * 8), ("wvs", C.c_void_p * 8), ("vss", C.c_void_p * 8),
-                    ("n_his", C.c_int), ("n_wvs", C.c_int), ("n_vss", C.c_int), ("wave_tmp", C.c_void_p),
-                    ("wave_tmp_width", C.c_uint32), ("n_interleave", C.c_int), ("i_interleave", C.c_int),
-                    ("interleave_rendered", C.c_bool)]
-
-    rendered_off = 3 * 56 + 12       # struct b200_cm_source: `rendered` follows queue[3] and the three indices
     rng = np.random.default_rng(11)
 
     # --- pacing: random sequences of ticks with 0..2 renders each ---
@@ -374,9 +290,13 @@ def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
         roi = Roi()
         lib.b200_roi_init(C.byref(roi), None, 1)
         roi.n_interleave = n_interleave
-        cm = C.create_string_buffer(4096)
+        cm_obj = S.CmSource()
+        cm = C.byref(cm_obj)
         lib.b200_cm_create(cm)
-        flag = C.c_bool.from_buffer(cm, rendered_off)
+
+        class _Flag:                                       # struct b200_cm_source.rendered
+            value = property(lambda self: cm_obj.rendered, lambda self, v: setattr(cm_obj, "rendered", v))
+        flag = _Flag()
         ticks = renders = 0
         for frame in range(60):
             flag.value = True                              # cm_tick resets it (common.c:216-221)
@@ -397,21 +317,16 @@ def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
     # --- clamping of the requested rectangle ---
     out = (C.c_int * 4)()
 
-    class CmTail(C.Structure):   # the last fields of struct b200_cm_source
-        _fields_ = [("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong), ("x0", C.c_int), ("x1", C.c_int),
-                    ("y0", C.c_int), ("y1", C.c_int)]
-
-    tail_off = 3 * 56 + 12 + 4 + 8 + 40 + 48 + 8 + 16 + 8     # flags_off (see above) + flags + colorspace
     for _ in range(300):
         w, h = int(rng.integers(1, 5000)), int(rng.integers(1, 3000))
         r = [int(v) for v in rng.integers(-50, 5200, 4)]
         if rng.random() < 0.3:
             r[int(rng.integers(0, 4))] = -1
-        cm = C.create_string_buffer(4096)
+        t = S.CmSource()
+        cm = C.byref(t)
         lib.b200_cm_create(cm)
         lib.b200_cm_set_roi(cm, r[0], r[1], r[2], r[3], w, h)
         L.ref_roi_send_range(r[0], r[1], r[2], r[3], w, h, out)
-        t = CmTail.from_buffer(cm, tail_off)
         assert (t.x0, t.y0, t.x1, t.y1) == tuple(out), (r, w, h)
         lib.b200_cm_destroy(cm)
 
@@ -456,22 +371,6 @@ def test_roi_pacing_clamp_and_flags_match_the_reference(shim, ref):
             lib.b200_roi_destroy(C.byref(roi))
 
 
-class _CmItem(C.Structure):   # include/cm_shim.h: struct b200_cm_queue_item
-    _fields_ = [("staged", C.c_void_p), ("staged_bytes", C.c_size_t), ("width", C.c_uint32),
-                ("height", C.c_uint32), ("linesize", C.c_uint32), ("flags", C.c_uint32),
-                ("colorspace", C.c_int), ("cb", C.c_void_p), ("cb_data", C.c_void_p)]
-
-
-class _Cm(C.Structure):       # include/cm_shim.h: struct b200_cm_source
-    _fields_ = [("queue", _CmItem * 3), ("i_write_queue", C.c_int), ("i_staging_queue", C.c_int),
-                ("i_read_queue", C.c_int), ("rendered", C.c_bool), ("pipeline_thread", C.c_ulong),
-                ("pipeline_mutex", C.c_byte * 40), ("pipeline_cond", C.c_byte * 48),
-                ("pipeline_thread_running", C.c_bool), ("request_exit", C.c_bool), ("worker_busy", C.c_bool),
-                ("callback", C.c_void_p), ("callback_data", C.c_void_p), ("flags", C.c_uint32),
-                ("colorspace", C.c_int), ("frames_dropped", C.c_ulong), ("frames_processed", C.c_ulong),
-                ("x0", C.c_int), ("x1", C.c_int), ("y0", C.c_int), ("y1", C.c_int)]
-
-
 @pytest.mark.parametrize("flags,roi", [(1, None), (3, None), (2, None), (3, (5, 3, 29, 17)), (1, (0, 0, 40, 9))])
 def test_capture_core_matches_the_reference(shim, pkg, flags, roi):
     """b200_cm_* against the reference's own capture core: src/common.c compiled unmodified on a software
@@ -493,8 +392,6 @@ def test_capture_core_matches_the_reference(shim, pkg, flags, roi):
     R.refc_set_roi.argtypes = [C.c_void_p] + [C.c_int] * 4
     R.refc_callbacks.restype = C.c_long
     R.refc_callbacks.argtypes = [C.c_void_p]
-    lib.b200_cm_set_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
-
     W, H = 40, 24
     gate = threading.Event()
     gate.set()
@@ -583,3 +480,45 @@ def test_capture_core_matches_the_reference(shim, pkg, flags, roi):
         assert seen["shim"][0][:2] == (roi[2] - roi[0], roi[3] - roi[1])
     lib.b200_cm_destroy(C.byref(cm))
     R.refc_free(ref)
+
+
+@pytest.mark.parametrize("scale", [2, 3, 5])
+def test_target_scale_is_staged_point_sampled(shim, pkg, oracle, scale):
+    """target_scale without a GPU attached: the staged surface is target size / scale (common.c:249-250), point-sampled
+    at the texel centres - the rule oracle/scope_oracle.c pins (orc_point_downsample) - and the ROI rectangle is in
+    pixels of that scaled surface (common.c:272-282)."""
+    lib = shim
+    W, H = 53, 38
+    rng = np.random.default_rng(scale)
+    rgb = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    yuv = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    small_rgb, small_yuv = oracle.downsample(rgb, scale), oracle.downsample(yuv, scale)
+    sw, sh = W // scale, H // scale
+    for rect in (None, (1, 2, sw - 1, sh - 1)):
+        cm_obj = S.CmSource()
+        cm = C.byref(cm_obj)
+        lib.b200_cm_create(cm)
+        cm_obj.flags, cm_obj.target_scale = 3, scale
+        got = []
+
+        def cb(_d, sd):
+            s = sd.contents
+            n = s.linesize * s.height
+            a = np.ctypeslib.as_array(C.cast(s.rgb_data, C.POINTER(C.c_uint8)), (n,)).copy()
+            b = np.ctypeslib.as_array(C.cast(s.yuv_data, C.POINTER(C.c_uint8)), (n,)).copy()
+            got.append((s.width, s.height, s.linesize, a, b, s.tex))
+
+        cfn = CB(cb)
+        lib.b200_cm_request(cm, cfn, None)
+        if rect:
+            lib.b200_cm_set_roi(cm, *rect, sw, sh)
+        for _ in range(2):
+            lib.b200_cm_tick(cm)
+            lib.b200_cm_render_target(cm, rgb.ctypes.data, yuv.ctypes.data, W * 4, W, H)
+            lib.b200_cm_drain(cm)
+        lib.b200_cm_destroy(cm)
+        w, h, ls, a, b, tex = got[0]
+        x0, y0, x1, y1 = rect if rect else (0, 0, sw, sh)
+        assert (w, h, ls) == (x1 - x0, y1 - y0, (x1 - x0) * 4) and not tex       # no hint without a GPU
+        assert np.array_equal(a.reshape(h, w, 4), small_rgb[y0:y1, x0:x1])
+        assert np.array_equal(b.reshape(h, w, 4), small_yuv[y0:y1, x0:x1])
