@@ -469,6 +469,112 @@ def run_b200_arm(args):
     eng.close()
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the page-locked frame buffers
+    allocated next come from that node's memory (first touch) and the copies do not cross the socket interconnect.
+    Returns what it did; a box with one node (or no sysfs entry) is left alone."""
+    import torch
+
+    info = {"gpu_node": None, "bound_cpus": None}
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["gpu_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["nodes"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["bound_cpus"] = len(allowed)
+    except Exception as e:   # context only
+        info["error"] = repr(e)[:120]
+    return info
+
+
+def run_e2e_shim(args, eng, st, host_ptr, nf, fbytes, dev, world):
+    """The same frames through the C shim a maintainer links (include/cm_shim.h): b200_cm_tick ->
+    b200_cm_render_target (zero-copy staging of the page-locked frame into queue slot = ring slot) -> the worker
+    thread -> b200_roi_surface_cb (one fused pass: submit frame n, file the results of frame n - 1 into the scopes'
+    double buffers).  A render that finds the worker busy is DROPPED by the capture core (common.c:260-268); the
+    driver below offers the frame again, so that every frame of the step is processed and the rate is comparable."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from obs_color_monitor_b200 import shim as S
+
+    W, H = args.width, args.height
+    lib, ctx = S.load(), eng.ctx.handle
+    cm, roi = S.CmSource(), S.RoiSource()
+    his, wvs, vss = S.HisSource(), S.WvsSource(), S.VssSource()
+    lib.b200_cm_create(C.byref(cm))
+    lib.b200_cm_attach_gpu(C.byref(cm), ctx, True)
+    cm.colorspace = st.colorspace
+    lib.b200_roi_init(C.byref(roi), ctx, 0)                 # SCOPE_MODE_FUSED
+    lib.b200_his_init(C.byref(his), ctx, 0x07)
+    lib.b200_wvs_init(C.byref(wvs), ctx, 0x07)
+    lib.b200_vss_init(C.byref(vss), ctx)
+    lib.b200_roi_register_his(C.byref(roi), C.byref(his))
+    lib.b200_roi_register_wvs(C.byref(roi), C.byref(wvs))
+    lib.b200_roi_register_vss(C.byref(roi), C.byref(vss))
+    cm.flags = lib.b200_roi_capture_flags(C.byref(roi)) & ~S.CM_FLAG_ROI
+    lib.b200_cm_request(C.byref(cm), C.cast(lib.b200_roi_surface_cb, C.c_void_p), C.cast(C.byref(roi), C.c_void_p))
+    retries = 0
+
+    def step():
+        nonlocal retries
+        for i in range(nf):
+            while True:
+                lib.b200_cm_tick(C.byref(cm))
+                if lib.b200_cm_render_target(C.byref(cm), host_ptr + i * fbytes, None, W * 4, W, H):
+                    break
+                retries += 1
+                time.sleep(0)
+        lib.b200_cm_drain(C.byref(cm))
+
+    def finish():
+        lib.b200_cm_tick(C.byref(cm))                       # the queue hands a surface to the worker one render late
+        while not lib.b200_cm_render_target(C.byref(cm), host_ptr, None, W * 4, W, H):
+            lib.b200_cm_tick(C.byref(cm))
+        lib.b200_cm_drain(C.byref(cm))
+        lib.b200_roi_finish(C.byref(roi))
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    filed0, retries = roi.frames_filed, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    finish()
+    dt = time.perf_counter() - t0
+    filed = roi.frames_filed - filed0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    import numpy as np
+    r = his.w_tex_buf ^ 1
+    hist = np.frombuffer((C.c_float * 1024).from_address(his.tex_buf[r]), dtype=np.float32)
+    ok = int(hist.sum()) == 3 * W * H
+    lib.b200_cm_destroy(C.byref(cm))
+    lib.b200_roi_destroy(C.byref(roi))
+    for d, src in ((lib.b200_his_destroy, his), (lib.b200_wvs_destroy, wvs), (lib.b200_vss_destroy, vss)):
+        d(C.byref(src))
+    return {"value": filed * world / dt, "unit": "frames/s", "frames_filed": int(filed), "renders_dropped_and_offered_again": retries,
+            "histogram_total_ok": ok,
+            "path": "b200_cm_tick -> b200_cm_render_target (zero-copy into queue slot = ring slot) -> worker thread -> "
+                    "b200_roi_surface_cb (submit frame n, file frame n-1 into the scopes' double buffers); wall clock"}
+
+
 def run_e2e(args, eng, st, batch, dev, world, rank):
     """Pinned host frames -> scope_submit_host (H2D + kernels + D2H on the slot's stream) ->
     scope_wait_host, three slots in flight like the reference's 3-deep stagesurface ring."""
@@ -484,6 +590,7 @@ def run_e2e(args, eng, st, batch, dev, world, rank):
     nf = min(args.e2e_frames, batch.shape[0])
     fbytes = W * H * 4
     lib = eng.lib
+    numa = bind_to_gpu_numa_node(dev.index if dev.index is not None else 0)
     ptr = lib.scope_host_alloc(nf * fbytes)
     if not ptr:
         return None
@@ -537,11 +644,17 @@ def run_e2e(args, eng, st, batch, dev, world, rank):
     dt = float(t.item())
     hist = np.ctypeslib.as_array((C.c_uint32 * 1024).from_address(res_ptr))
     assert int(hist.sum()) == 3 * W * H, "e2e histogram total is wrong"
+    shim_leg = None
+    try:
+        shim_leg = run_e2e_shim(args, eng, st, ptr, nf, fbytes, dev, world)
+    except Exception as e:   # context: never a reason to lose the bench line
+        shim_leg = {"error": repr(e)[:200]}
     lib.scope_host_free(ptr)
     lib.scope_host_free(res_ptr)
     out = {"value": nf * world * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": nf * fbytes,
            "d2h_bytes_per_step": nf * (4096 + 16 + 65536 + wave_bytes), "frames_per_step": nf,
-           "path": "scope_submit_host/scope_wait_host, 3-slot ring, pinned host frames, wall clock max over ranks"}
+           "path": "scope_submit_host/scope_wait_host, 3-slot ring, pinned host frames, wall clock max over ranks",
+           "shim": shim_leg, "numa": numa}
     # what bounds this path: the host->device copy of the frames.  Measure the box's pinned H2D bandwidth
     # (plain copy, nothing else running) so that the e2e number can be read against ITS roofline.
     try:
@@ -657,25 +770,28 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
                 torch.cuda.synchronize()
                 bad += int(not torch.equal(outs[j]["wave"][0], ref["wave"][0]))
         parity = {"checked_frames": 2 if (bands == "cols" or world == 1) else 0, "mismatches": bad}
-    launches_per_frame, graphs = None, None
+    launches_per_frame, big = None, None
     use_graph = graph and not (reduce == "nccl" and world > 1)
     graph_error = None
+    G = 8    # frames per graph replay: both streams inside ONE graph (fork / join), so that the host's graph-launch
+             # rate (a few tens of microseconds per replay from Python) cannot be what a 20-microsecond frame waits for
     if use_graph:
         try:
-            graphs = {}
-            for j in range(2):
-                for k in range(4):
-                    if (k % 2) != j:
-                        continue
-                    g = torch.cuda.CUDAGraph()
-                    l_before = eng.launch_count
-                    with torch.cuda.graph(g, stream=streams[j]):
-                        enqueue(j, k)
-                    launches_per_frame = eng.launch_count - l_before
-                    graphs[k] = g
-            for i in range(8):
-                with torch.cuda.stream(streams[i % 2]):
-                    graphs[i % 4].replay()
+            big = torch.cuda.CUDAGraph()
+            l_before = eng.launch_count
+            fork, joined = torch.cuda.Event(), torch.cuda.Event()
+            with torch.cuda.graph(big, stream=streams[0]):
+                fork.record(streams[0])
+                streams[1].wait_event(fork)
+                for i in range(G):
+                    with torch.cuda.stream(streams[i % 2]):
+                        enqueue(i % 2, i % 4)
+                joined.record(streams[1])
+                streams[0].wait_event(joined)
+            launches_per_frame = (eng.launch_count - l_before) / G
+            for _ in range(2):
+                with torch.cuda.stream(streams[0]):
+                    big.replay()
             barrier()
         except Exception as e:      # a capture that fails on one rank must not hang the others: fall back together
             graph_error = repr(e)[:200]
@@ -684,13 +800,29 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
             flag = torch.tensor([0 if use_graph else 1], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
             use_graph = use_graph and int(flag.item()) == 0
+    if use_graph:
+        steps = max(G, steps // G * G)
 
     def step(i):
+        if use_graph:
+            if i % G == 0:
+                with torch.cuda.stream(streams[0]):
+                    big.replay()
+            return
         with torch.cuda.stream(streams[i % 2]):
-            if use_graph:
-                graphs[i % 4].replay()
-            else:
-                enqueue(i % 2, i % 4)
+            enqueue(i % 2, i % 4)
+
+    # the accumulation kernel alone (this rank's band, stream 0, events around single launches): what the frame time
+    # is made of besides it is the cross-rank step and whatever the two streams do not overlap
+    eng.ctx.profile_enable(True)
+    eng.ctx.profile_read()
+    with torch.cuda.stream(streams[0]):
+        for i in range(6):
+            ring[0].accumulate(data[i % 4], width=width)
+    barrier()
+    kms = eng.ctx.profile_read()
+    eng.ctx.profile_enable(False)
+    kernel_us = 1e3 * sorted(kms)[len(kms) // 2] if kms else None
 
     sampler = ClockSampler(dev.index if dev.index is not None else 0)
     if rank == 0:
@@ -730,7 +862,9 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         "metric": "frames/sec ROI-tiled waveform (luma) @7680x4320 BGRA", "value": steps / (ms * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": steps, "warmup": max(warmup, 4), "ms_per_frame": ms / steps, "bands": bands,
         "reduce": reduce if world > 1 else "none (one rank)", "graph": bool(use_graph), "graph_error": graph_error,
-        "frames_in_flight": 2,
+        "frames_in_flight": 2, "frames_per_graph": G if use_graph else None,
+        "band_kernel_us": kernel_us,
+        "band_bytes": W * H * 4 // world,
         "bytes_over_nvlink_per_rank_per_frame": int(nvlink),
         "gpu_launches_per_frame": launches_per_frame if launches_per_frame is not None else (eng.launch_count - l0) / steps,
         "achieved_read_GBps_all_ranks": steps * W * H * 4 / (ms * 1e-3) / 1e9, "clocks": clocks, "parity": parity,
@@ -805,6 +939,10 @@ def run_stream_vscope(args):
         res = eng.accumulate_host(host[i % nf], settings=st)
         lat.append(time.perf_counter() - t0)
     n = 60 * max(args.steps, 1)
+    sampler = ClockSampler(0)
+    sampler.start()
+    eng.ctx.profile_enable(True)
+    eng.ctx.profile_read()
     t0 = time.perf_counter()
     for i in range(n):
         sl = i % 3
@@ -814,9 +952,30 @@ def run_stream_vscope(args):
     for i in range(n - 3, n):
         res = eng.wait_host(i % 3)
     dt = time.perf_counter() - t0
+    kernel_ms = eng.ctx.profile_read()
+    eng.ctx.profile_enable(False)
+    clocks = sampler.stop()
     assert res["vscope"].max() > 0 and res["vscope_display"].max() == 255
+    # parity of the last frames against the oracle (outside the timed region)
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    bad = 0
+    for i in range(2):
+        f = np.ascontiguousarray(host[i])
+        r = eng.accumulate_host(f, settings=st)
+        vs = orc.vectorscope(orc.rgb_to_yuv(f, args.colorspace))
+        bad += int(not np.array_equal(r["vscope"], vs)) + int(not np.array_equal(r["vscope_display"], orc.apply_intensity(vs, 25)))
     lib.scope_host_free(ptr)
+    peak, peak_src = _hbm_peak()
+    k_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+    achieved = W * H * 4 / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     print(json.dumps({
+        "clocks": clocks, "parity": {"checked_frames": 2, "mismatches": bad},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "kernel": "the strip kernel of the vectorscope-only pass, one frame per launch", "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": W * H * 4, "peak_source": peak_src, "traffic": None,
+                     "note": "one 33 MB frame per launch (148 CTAs x ~0.8 strips): launch-latency sized; the stream "
+                             "itself is bound by the host->device copy, see value"},
         "metric": "frames/sec vectorscope+intensity stream @3840x2160 BGRA (host ring)", "value": n / dt,
         "unit": "frames/s", "n_gpus": 1, "steps": n, "warmup": 6, "ms_per_step": 1e3 * dt / n,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",

@@ -70,18 +70,6 @@ struct V3 {
 // ---------------------------------------------------------------------------
 // helpers (each with its emulated twin, like the ones in scope_kernels.cuh)
 // ---------------------------------------------------------------------------
-// (hi : lo) >> n, low 32 bits
-__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t n)
-{
-#ifdef SCOPE_EMULATE
-	return (uint32_t)((((uint64_t)hi << 32) | lo) >> n);
-#else
-	uint32_t d;
-	asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(n));
-	return d;
-#endif
-}
-
 // two fp32 lanes in one 64-bit value
 struct F2 {
 #ifdef SCOPE_EMULATE
@@ -183,7 +171,7 @@ __device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b)
 constexpr uint32_t kV3UBias = 65536u - V3::kVStride * V3::kVMin; // 61376: makes the low 16 bits of 260 V + U come out as U + 260 (V - 16)
 struct V3Coef {
 	uint32_t u[3], v[3]; // 10^6 x the effect file's coefficients, order R, G, B
-	uint32_t ku, kv;     // rounding/offset constants + 0xC0000000 (the two bits the funnel shift turns into exponent bits)
+	uint32_t ku, kv;     // rounding/offset constants incl. kDivExpBits (Coef)
 };
 template <int CS>
 __device__ __forceinline__ constexpr V3Coef v3_coef()
@@ -194,8 +182,8 @@ __device__ __forceinline__ constexpr V3Coef v3_coef()
 		r.u[i] = c.u[i];
 		r.v[i] = c.v[i];
 	}
-	r.ku = c.ku + 0xC0000000u;
-	r.kv = c.kv + 0xC0000000u;
+	r.ku = c.ku;
+	r.kv = c.kv;
 	return r;
 }
 inline V3Coef v3_coef_for(int colorspace)
@@ -206,8 +194,8 @@ inline V3Coef v3_coef_for(int colorspace)
 		r.u[i] = c.u[i];
 		r.v[i] = c.v[i];
 	}
-	r.ku = c.ku + 0xC0000000u;
-	r.kv = c.kv + 0xC0000000u;
+	r.ku = c.ku;
+	r.kv = c.kv;
 	return r;
 }
 

@@ -173,6 +173,14 @@ constexpr int kMaxChunkItems = SCOPE_MAX_CHUNK; // upper bound of strips per dyn
 // its first tile was handed back, so it is at most kStages chunks ahead of the slowest consumer (chunks
 // of one single-tile strip): kQueue >= kStages (tools/ring_model.py checks the mailbox as well).
 constexpr int kQueue = SCOPE_DEEP_RING ? 8 : 4;
+#ifndef SCOPE_L2_AHEAD
+#define SCOPE_L2_AHEAD 0
+#endif
+constexpr int kL2Ahead = SCOPE_L2_AHEAD;   // tiles the general producer's L2 prefetch runs ahead of its TMA loads.  0: none -
+                                           // measured with 6: waveform-only 71.0 -> 64.8 %, histogram-only 66.4 -> 58.8 %,
+                                           // vectorscope-only 46.4 -> 43.6 % of the HBM peak (these kernels already keep
+                                           // 64 KB in flight per SM, or are bound elsewhere); only scope_fused_kernel_v3,
+                                           // whose ring is 35 KB, gains from it (SCOPE_V3_L2_AHEAD)
 constexpr int kLdgWarps = 16;              // plain-load fallback kernel
 constexpr int kLdgRows = 4;
 constexpr int kMaxWaveCopies = 15;    // extra destinations of the final waveform (scope_accumulate_band: <= 16 ranks)
@@ -396,6 +404,45 @@ __device__ __forceinline__ void ldsm_rows(uint32_t rows_addr, int lane, uint32_t
 // instead of the half-rate FMA-heavy (IMAD) or ALU (LEA) pipes that bound the inner loop.
 constexpr uint32_t kCarrierBias = SCOPE_FADDR ? 0u : 0x4B000000u;
 
+// Division by 10^6 on the FMA pipe (round 2: IMAD.HI occupies the FMA-heavy pipe like four IMADs, tools/ubench3.cu).
+// S < 2^28 is exact; 10^6 = 64 * 15625, so floor(S / 10^6) = floor(T / 15625) with T = S >> 6 < 2^22.  The sums carry
+// kDivExpBits = 0xC0000000 in their constant: a funnel shift by 6 with 0x12 in the upper word then yields the bit
+// pattern 0x4B000000 | T, i.e. the float 2^23 + T, without a conversion.  q = round((T - 7812) / 15625) = floor(T / 15625)
+// comes out of one add (exact) and one fused multiply-add whose addend 1.5 * 2^23 puts the sum where the ulp is 1: the
+// result's bit pattern is 0x4B400000 + q.  The product's rounding error is < 1.7e-5, the distance of (T - 7812) / 15625
+// from a half-integer >= 3.2e-5.  Checked for all 2^24 colours and both colour spaces against the oracle.
+constexpr uint32_t kDivExpBits = 0xC0000000u;
+constexpr uint32_t kDivFunnelHi = 0x12u;
+// (hi : lo) >> n, low 32 bits
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t n)
+{
+#ifdef SCOPE_EMULATE
+	return (uint32_t)((((uint64_t)hi << 32) | lo) >> n);
+#else
+	uint32_t d;
+	asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(n));
+	return d;
+#endif
+}
+
+// 0x4B400000 + floor(S / 10^6) from a sum S that carries kDivExpBits; `round_to` = 1.5 * 2^23 (+ a bias the caller wants
+// in the result)
+__device__ __forceinline__ uint32_t div_1e6_bits(uint32_t s, float round_to)
+{
+#ifdef SCOPE_EMULATE
+	uint32_t t = funnel_r(s, kDivFunnelHi, 6u);
+	float tf;
+	memcpy(&tf, &t, 4);
+	const float d = std::fmaf(tf + -(8388608.0f + 7812.0f), 1.0f / 15625.0f, round_to);
+	uint32_t r;
+	memcpy(&r, &d, 4);
+	return r;
+#else
+	const float tf = __uint_as_float(funnel_r(s, kDivFunnelHi, 6u));
+	return __float_as_uint(__fmaf_rn(__fadd_rn(tf, -(8388608.0f + 7812.0f)), 1.0f / 15625.0f, round_to));
+#endif
+}
+
 // (host side)
 // 10^6 x the coefficients printed in data/common.effect:27-29 (BT.601) and :38-40 (BT.709), as
 // integers, order R, G, B; K = floor(10^6 * (255 * off + 1/2)) with off = 1/2 - 1/256 (U), 0 (Y),
@@ -407,7 +454,7 @@ inline Coef coef_for(int colorspace)
 					   {+437500, -366351, -71147}};
 	static const int32_t k709[3][3] = {{-100643, -338571, +439216}, {+212600, +715200, +72200},
 					   {+439216, -398941, -40273}};
-	static const uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
+	static const uint32_t k_add[3] = {127003906u + kDivExpBits, 500000u + kDivExpBits, 128000000u + kDivExpBits};
 	const int32_t(*m)[3] = colorspace == 1 ? k601 : k709;
 	Coef c;
 	uint32_t *rows[3] = {c.u, c.y, c.v};
@@ -430,7 +477,7 @@ __device__ __forceinline__ constexpr Coef const_coef()
 	constexpr int32_t m[3][3] = {{CS == 1 ? -147643 : -100643, CS == 1 ? -289855 : -338571, CS == 1 ? 437500 : 439216},
 				     {CS == 1 ? 299000 : 212600, CS == 1 ? 587000 : 715200, CS == 1 ? 114000 : 72200},
 				     {CS == 1 ? 437500 : 439216, CS == 1 ? -366351 : -398941, CS == 1 ? -71147 : -40273}};
-	constexpr uint32_t k_add[3] = {127003906u, 500000u, 128000000u};
+	constexpr uint32_t k_add[3] = {127003906u + kDivExpBits, 500000u + kDivExpBits, 128000000u + kDivExpBits};
 	Coef c{};
 	for (int i = 0; i < 3; i++) {
 		c.u[i] = (uint32_t)m[0][i];
@@ -513,25 +560,27 @@ __device__ __forceinline__ uint32_t yuv_channel(const uint32_t (&bgr)[3], const 
 	uint32_t s = bgr[2] * c[0] + k;
 	s = bgr[1] * c[1] + s;
 	s = bgr[0] * c[2] + s;
-	return __umulhi(s, kDivMagic);
+	// q in BYTE 2 (bytes 0, 1, 3 zero): (0x4B400000 + q) << 16 = q << 16 mod 2^32
+	return div_1e6_bits(s, 12582912.0f) << 16;
 }
 
 // B, G, R carriers of one pixel -> U, (Y), V, each in byte 2 of its word (bytes 3 = 0)
+// `need`: bit 0 U, bit 1 Y, bit 2 V (launch-uniform: a luma-only waveform - BASELINE config 4 - evaluates one channel, not three)
 template <bool NEED_Y>
-__device__ __forceinline__ void rgb_to_yuv_hi(const uint32_t (&bgr)[3], const Coef &c, uint32_t (&hi)[3])
+__device__ __forceinline__ void rgb_to_yuv_hi(const uint32_t (&bgr)[3], const Coef &c, uint32_t (&hi)[3], uint32_t need = 7u)
 {
-	hi[0] = yuv_channel(bgr, c.u, c.ku);
-	hi[1] = NEED_Y ? yuv_channel(bgr, c.y, c.ky) : 0u;
-	hi[2] = yuv_channel(bgr, c.v, c.kv);
+	hi[0] = (need & 1u) ? yuv_channel(bgr, c.u, c.ku) : 0u;
+	hi[1] = (NEED_Y && (need & 2u)) ? yuv_channel(bgr, c.y, c.ky) : 0u;
+	hi[2] = (need & 4u) ? yuv_channel(bgr, c.v, c.kv) : 0u;
 }
 
 // the same, as carriers of U, Y, V
 template <bool NEED_Y>
 __device__ __forceinline__ void rgb_to_yuv_carriers(const uint32_t (&bgr)[3], const Coef &c, uint32_t magic,
-						     uint32_t (&yuv)[3])
+						     uint32_t (&yuv)[3], uint32_t need = 7u)
 {
 	uint32_t hi[3];
-	rgb_to_yuv_hi<NEED_Y>(bgr, c, hi);
+	rgb_to_yuv_hi<NEED_Y>(bgr, c, hi, need);
 	yuv[0] = carrier<2>(hi[0], magic);
 	yuv[1] = NEED_Y ? carrier<2>(hi[1], magic) : 0u;
 	yuv[2] = carrier<2>(hi[2], magic);
@@ -767,9 +816,10 @@ __device__ __forceinline__ void process_tile(const TileCtx &c, const Coef &coef,
 					cyuv[k][j] = uyv[j] + kCarrierBias;
 			}
 		} else {
+			const uint32_t need = VSCOPE ? (c.bins_mask | 5u) : c.bins_mask;
 #pragma unroll
 			for (int k = 0; k < N; k++)
-				rgb_to_yuv_carriers<SRC == SRC_YUV>(crgb[k], coef, c.magic, cyuv[k]);
+				rgb_to_yuv_carriers<SRC == SRC_YUV>(crgb[k], coef, c.magic, cyuv[k], need);
 		}
 	} else if (SURFACE && SRC == SRC_YUV) {
 #pragma unroll
@@ -1115,9 +1165,10 @@ __device__ __forceinline__ void prepare_tile(const TileCtx &c, const Coef &coef,
 		}
 	}
 	if (kTransform) {
+		const uint32_t need = VSCOPE ? (c.bins_mask | 5u) : c.bins_mask;
 #pragma unroll
 		for (int k = 0; k < N; k++)
-			rgb_to_yuv_hi<SRC == SRC_YUV>(crgb[k], coef, hi[k]);
+			rgb_to_yuv_hi<SRC == SRC_YUV>(crgb[k], coef, hi[k], need);
 	}
 	o.all_counted = true;
 	if (SRC != SRC_NONE) {
@@ -1334,10 +1385,28 @@ __device__ __forceinline__ void tma_produce(const StripParams &P, const CUtensor
 			mbar_arrive(bar_full + 8 * stage); // wake the consumers with no data
 			break;
 		}
+		// L2 prefetch cursor (off by default, see kL2Ahead): runs kL2Ahead tiles ahead of the loads inside this chunk
+		uint32_t pf_item = first, pf_t = 0;
+		auto prefetch_to = [&](uint32_t item, uint32_t t) {
+			const uint32_t goal = (item - first) * tiles + t + (uint32_t)kL2Ahead;
+			while (pf_item < last && (pf_item - first) * tiles + pf_t <= goal) {
+				const uint32_t f = pf_item / P.strips, st = pf_item - f * P.strips;
+				if (L::kLoadRgb)
+					tma_prefetch_3d(map_rgb, (int)(st * kStripPx + P.tma_x0_rgb), (int)(pf_t * L::kTileRows), (int)f);
+				if (L::kLoadYuv)
+					tma_prefetch_3d(map_yuv, (int)(st * kStripPx + P.tma_x0_yuv), (int)(pf_t * L::kTileRows), (int)f);
+				if (++pf_t == tiles) {
+					pf_t = 0;
+					pf_item++;
+				}
+			}
+		};
 		for (uint32_t item = first; item < last; item++) {
 			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
 			const int x = (int)(strip * kStripPx);
 			for (uint32_t t = 0; t < tiles; t++) {
+				if (kL2Ahead > 0)
+					prefetch_to(item, t);
 				if (!(item == first && t == 0))
 					mbar_wait(bar_empty + 8 * stage, phase ^ 1);
 				const uint32_t dst = smem_base + L::kStageOff + stage * L::kStageBytes;
@@ -1622,9 +1691,11 @@ __device__ __forceinline__ void tma_setup(uint8_t *smem, uint32_t bar_full, uint
 // of each 64-row tile; 1 producer warp.  Used for all scope combinations except the one below.
 // ---------------------------------------------------------------------------
 // Without the vectorscope's 128 KB of bins two CTAs fit in an SM's shared memory; the register
-// budget is then 56 per thread (34 warps), which the kernels without a colour transform meet.
+// budget is then 56 per thread (34 warps).  Since round 2 the kernels WITH a colour transform meet it as well
+// (coefficients as immediates, division by 10^6 on the FMA pipe, only the channels the launch needs): the
+// luma-only waveform of BASELINE config 4 runs two CTAs per SM = 64 KB of tiles in flight instead of 32.
 template <int SRC, bool VSCOPE, bool SURFACE>
-constexpr int kTmaMinCtas = (!VSCOPE && (SRC == SRC_RGB || SURFACE)) ? 2 : 1;
+constexpr int kTmaMinCtas = !VSCOPE ? 2 : 1;
 
 // SCOPE_MAXNREG (experiment): an explicit register cap instead of the one ptxas derives from the launch bounds
 // (for 544 threads it stops at 96, not at the 120 that fit: it seems to round the block up to 640 threads);
