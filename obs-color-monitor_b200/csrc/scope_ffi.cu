@@ -313,6 +313,7 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 	P.coef = coef_for(rq.colorspace);
 	P.scale_x = rq.scale_x;
 	P.scale_y = rq.scale_y;
+	v3_param_consts(P.v3c);
 	P.xform_strict = rq.strict ? 1u : 0u;
 	P.colorspace = rq.colorspace;
 

@@ -37,10 +37,13 @@ namespace scope {
 #define SCOPE_V3_WARPS 23
 #endif
 #ifndef SCOPE_V3_STAGES
-#define SCOPE_V3_STAGES 3
+#define SCOPE_V3_STAGES 4
 #endif
 #ifndef SCOPE_V3_L2_AHEAD
 #define SCOPE_V3_L2_AHEAD 6 // tiles the producer's L2 prefetch runs ahead of its loads (0: none)
+#endif
+#ifndef SCOPE_V3_PARAM_CONSTS
+#define SCOPE_V3_PARAM_CONSTS 1 // the kernel's constants come from the launch parameters (0: immediates, A/B partner)
 #endif
 #ifndef SCOPE_V3_FFMA2
 #define SCOPE_V3_FFMA2 1 // 0: scalar FFMA / FADD (A/B partner)
@@ -53,9 +56,18 @@ struct V3 {
 	static constexpr int kTileBytes = kTileRows * kStripPx * 4;
 	static constexpr int kStages = SCOPE_V3_STAGES;
 	static constexpr int kThreads = (kWarps + 1) * 32;
-	static constexpr int kVsOff = 0;
-	static constexpr int kWaveOff = kVsWords * 4;
-	static constexpr int kStageOff = kWaveOff + 2 * kWaveWords * 4;
+	// vectorscope table: bin (U, V) lives in word (U & 127) + 132 V, half U >> 7.  V of the fused transform lies in
+	// [16, 240] for every colour (tests/test_oracle.py), so only words [132 * 16, 132 * 241) exist: 29 700 words =
+	// 116 KB instead of 128 KB, which is what pays for the ring's fourth stage.  The stride 132 = 128 + 4 makes the
+	// bank (U + 4 V) mod 32 - the additive swizzle - and keeps a word's two bins 128 U apart (neighbouring colours
+	// never share a word: same-word lanes serialise like bank conflicts do).
+	static constexpr uint32_t kVStride = 132, kVMin = 16, kVMax = 240;
+	static constexpr int kVsFirstWord = kVStride * kVMin;                   // 2112
+	static constexpr int kVsTableWords = (kVStride * (kVMax + 1) - kVsFirstWord + 3) / 4 * 4; // 29 700
+	static constexpr int kWaveOff = 0;
+	static constexpr int kVsOff = 2 * kWaveWords * 4;                       // behind the column bins
+	static_assert(kVsOff >= kVsFirstWord * 4, "the table's virtual base (kVsOff - 4 * kVsFirstWord) must not be negative");
+	static constexpr int kStageOff = (kVsOff + kVsTableWords * 4 + 127) / 128 * 128;
 	static constexpr int kBarOff = kStageOff + kStages * kTileBytes;
 	static constexpr int kQueueOff = kBarOff + 2 * 8 * kStages + 16;
 	static constexpr int kTotal = kQueueOff + kQueue * 8 + 16;
@@ -63,8 +75,6 @@ struct V3 {
 #ifndef SCOPE_EMULATE // (the emulation tests build a copy with a one-entry mailbox on purpose)
 	static_assert(kStages <= kQueue, "chunk mailbox shorter than the ring");
 #endif
-	// vectorscope bin index = U + kVStride * (V - kVMin)
-	static constexpr uint32_t kVStride = 260, kVMin = 16;
 };
 
 // ---------------------------------------------------------------------------
@@ -168,7 +178,7 @@ __device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b)
 // ---------------------------------------------------------------------------
 // the transform: B, G, R bytes (plain integers) -> bit patterns 0x4B400000 + 61376 + U and 0x4B400000 + V
 // ---------------------------------------------------------------------------
-constexpr uint32_t kV3UBias = 65536u - V3::kVStride * V3::kVMin; // 61376: makes the low 16 bits of 260 V + U come out as U + 260 (V - 16)
+constexpr uint32_t kV3UBias = 0u; // (no bias on U in the float result any more)
 struct V3Coef {
 	uint32_t u[3], v[3]; // 10^6 x the effect file's coefficients, order R, G, B
 	uint32_t ku, kv;     // rounding/offset constants incl. kDivExpBits (Coef)
@@ -205,10 +215,42 @@ struct V3Consts {
 	F2 round;    // (1.5 * 2^23 + 61376, 1.5 * 2^23)
 	F2 k128;     // 128.0 x 2
 	F2 wb0, wb1; // this lane's plane-0 / plane-1 base address x 2
-	F2 vs_mul;   // (4.0, 65535 / 32768)
-	F2 vs_add;   // (vectorscope base address, 1)
+	F2 vs_mul;   // (4.0, 65535 / 128)
+	F2 vs_add;   // (address word 0 of the vectorscope table WOULD have, 1)
 	uint32_t exp_hi; // 0x12: the upper bits of the funnel shift
 };
+// the values of StripParams::v3c (host side)
+inline void v3_param_consts(uint32_t (&c)[8])
+{
+	auto bits = [](float f) {
+		uint32_t r;
+		memcpy(&r, &f, 4);
+		return r;
+	};
+	c[0] = bits(12582912.0f + (float)kV3UBias);
+	c[1] = bits(12582912.0f);
+	c[2] = bits(4.0f);
+	c[3] = bits(65535.0f / 128.0f);
+	c[4] = bits(1.0f / 15625.0f);
+	c[5] = bits(-(8388608.0f + 7812.0f));
+	c[6] = bits(128.0f);
+	c[7] = 0x12u;
+}
+__device__ __forceinline__ V3Consts v3_consts_from(const uint32_t (&pc)[8], uint32_t smem_base, int lane)
+{
+	V3Consts c;
+	c.neg_bias = f2_pack(pc[5], pc[5]);
+	c.inv = f2_pack(pc[4], pc[4]);
+	c.round = f2_pack(pc[0], pc[1]);
+	c.k128 = f2_pack(pc[6], pc[6]);
+	const uint32_t w0 = smem_base + V3::kWaveOff + lane * 4;
+	c.wb0 = f2_pack(w0, w0);
+	c.wb1 = f2_pack(w0 + kWaveWords * 4, w0 + kWaveWords * 4);
+	c.vs_mul = f2_pack(pc[2], pc[3]);
+	c.vs_add = f2_pack(smem_base + V3::kVsOff - 4u * V3::kVsFirstWord, 1u);
+	c.exp_hi = pc[7];
+	return c;
+}
 __device__ __forceinline__ V3Consts v3_consts(uint32_t smem_base, int lane)
 {
 	V3Consts c;
@@ -222,8 +264,8 @@ __device__ __forceinline__ V3Consts v3_consts(uint32_t smem_base, int lane)
 	const uint32_t w0 = smem_base + V3::kWaveOff + lane * 4;
 	c.wb0 = f2_pack(w0, w0);
 	c.wb1 = f2_pack(w0 + kWaveWords * 4, w0 + kWaveWords * 4);
-	c.vs_mul = f2_pack(f32_bits(4.0f), f32_bits(65535.0f / 32768.0f));
-	c.vs_add = f2_pack(smem_base + V3::kVsOff, 1u);
+	c.vs_mul = f2_pack(f32_bits(4.0f), f32_bits(65535.0f / 128.0f));
+	c.vs_add = f2_pack(smem_base + V3::kVsOff - 4u * V3::kVsFirstWord, 1u);
 	c.exp_hi = 0x12u;
 	return c;
 }
@@ -249,8 +291,10 @@ __device__ __forceinline__ void v3_vs_target(const F2 &uv, const V3Consts &k, ui
 {
 	uint32_t ru, rv;
 	f2_unpack(uv, ru, rv);
-	const uint32_t idx = rv * V3::kVStride + ru; // low 16 bits: U + 260 (V - 16)
-	const F2 t = f2_fma(f2_pack(idx & 0x7FFFu, idx & 0x8000u), k.vs_mul, k.vs_add);
+	// word = (U & 127) + 132 V: ONE IMAD on the two float bit patterns (0x4B400000 + U with bit 7 cleared, 0x4B400000 + V;
+	// the biases add up to a multiple of 2^22); half = bit 7 of U
+	const uint32_t idx = rv * V3::kVStride + (ru & ~0x80u);
+	const F2 t = f2_fma(f2_pack(idx & 0xFFFFu, ru & 0x80u), k.vs_mul, k.vs_add);
 	f2_unpack(t, addr, add);
 }
 
@@ -424,13 +468,14 @@ __device__ __forceinline__ void v3_block_slow(const uint32_t (&p)[4], const V3Co
 // ---------------------------------------------------------------------------
 // vectorscope flush: the consumer warps move the u16 halves to the frame's u32 accumulators
 // ---------------------------------------------------------------------------
-// bin index -> offset in the frame's u32 accumulators (row = 255 - V, vectorscope.c:232); the four slots per 260
-// that hold no bin are never written
-__device__ __forceinline__ uint32_t v3_acc_offset(uint32_t idx)
+// table word (0-based inside the table) + half -> offset in the frame's u32 accumulators (row = 255 - V,
+// vectorscope.c:232); the four slots per 132 that hold no bin are never written
+__device__ __forceinline__ uint32_t v3_acc_offset(uint32_t word, uint32_t half)
 {
-	const uint32_t vq = ((idx >> 2) * 64528u) >> 22; // idx / 260 for idx < 65536
-	const uint32_t u = idx - vq * V3::kVStride;
-	return (255u - V3::kVMin - vq) * 256u + u;
+	const uint32_t w = word + V3::kVsFirstWord;
+	const uint32_t v = ((w >> 2) * 1986u) >> 16; // w / 132 for w < 32768
+	const uint32_t u = w - v * V3::kVStride + 128u * half;
+	return (255u - v) * 256u + u;
 }
 
 __device__ __forceinline__ void v3_flush(const StripParams &P, uint32_t *vs, uint32_t frame, int tid)
@@ -438,12 +483,12 @@ __device__ __forceinline__ void v3_flush(const StripParams &P, uint32_t *vs, uin
 	constexpr int kStep = V3::kWarps * 32, kBatch = 4;
 	workers_bar<V3::kWarps>();
 	uint32_t *acc = P.vscope_acc + (size_t)frame * P.vscope_stride;
-	for (int i0 = tid; i0 < kVsWords / 4; i0 += kBatch * kStep) {
+	for (int i0 = tid; i0 < V3::kVsTableWords / 4; i0 += kBatch * kStep) {
 		uint4 wv[kBatch];
 #pragma unroll
 		for (int b = 0; b < kBatch; b++) {
 			const int i = i0 + b * kStep;
-			wv[b] = i < kVsWords / 4 ? reinterpret_cast<uint4 *>(vs)[i] : make_uint4(0, 0, 0, 0);
+			wv[b] = i < V3::kVsTableWords / 4 ? reinterpret_cast<uint4 *>(vs)[i] : make_uint4(0, 0, 0, 0);
 		}
 #pragma unroll
 		for (int b = 0; b < kBatch; b++) {
@@ -455,9 +500,9 @@ __device__ __forceinline__ void v3_flush(const StripParams &P, uint32_t *vs, uin
 				for (int j = 0; j < 4; j++) {
 					const uint32_t word = (uint32_t)i * 4u + (uint32_t)j;
 					if (ww[j] & 0xFFFFu)
-						atomicAdd(acc + v3_acc_offset(word), ww[j] & 0xFFFFu);
+						atomicAdd(acc + v3_acc_offset(word, 0u), ww[j] & 0xFFFFu);
 					if (ww[j] >> 16)
-						atomicAdd(acc + v3_acc_offset(word + 32768u), ww[j] >> 16);
+						atomicAdd(acc + v3_acc_offset(word, 1u), ww[j] >> 16);
 				}
 				reinterpret_cast<uint4 *>(vs)[i] = make_uint4(0, 0, 0, 0);
 			}
@@ -688,18 +733,22 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 					   volatile uint32_t *chunk_q, uint32_t bar_full, uint32_t bar_empty, int warp, int lane,
 					   int tid)
 {
-	static_assert(V3::kStages == 3, "v3_consume is unrolled for three stages");
+	static_assert(V3::kStages == 3 || V3::kStages == 4, "v3_consume is unrolled for three or four stages");
 	uint32_t *vs = reinterpret_cast<uint32_t *>(smem + V3::kVsOff);
 	uint32_t *wave0 = reinterpret_cast<uint32_t *>(smem + V3::kWaveOff);
 	const uint32_t tiles = (P.height + V3::kTileRows - 1) / V3::kTileRows;
 	constexpr V3Coef coef = v3_coef<CS>();
 	V3Warp w;
+	// (the addends of the two sums stay in registers: an IMAD takes one immediate, the multiplier)
+#if SCOPE_V3_PARAM_CONSTS
+	w.k = v3_consts_from(P.v3c, smem_base, lane);
+	w.ku = P.coef.ku;
+	w.kv = P.coef.kv;
+	(void)coef;
+#else
 	w.k = v3_consts(smem_base, lane);
-	// (kept in registers: an IMAD takes one immediate, the multiplier)
 	w.ku = coef.ku;
 	w.kv = coef.kv;
-#ifndef SCOPE_EMULATE
-	asm volatile("" : "+r"(w.ku), "+r"(w.kv));
 #endif
 	w.zero = P.rt_zero; // 0, known only at run time (see StripParams)
 	w.rows_base = smem_base + V3::kStageOff + (uint32_t)warp * (V3::kRows * kStripPx * 4) + (uint32_t)lane * 16u;
@@ -746,16 +795,28 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 			uint32_t n_fast = 0;
 			if (strip_full && P.height >= w.y_warp + V3::kRows)
 				n_fast = (P.height - w.y_warp - V3::kRows) / V3::kTileRows + 1u;
-			uint32_t pa[4], pb[4], pc[4];
+			uint32_t pa[4], pb[4], pc[4], pd[4];
 			// tile 0 (the chunk announcement already waited for the first item's)
 			v3_load<0>(w, ph, pa, item != first);
 			v3_release<0>(w, pa);
-			for (uint32_t t = 0; t < tiles; t += 3) { // sass-loop-v3
-				v3_visit<CS, 0>(P, w, ph, t, tiles, n_fast, lane_ok, pa, pb, pend);
-				if (t + 1 < tiles)
-					v3_visit<CS, 1>(P, w, ph, t + 1, tiles, n_fast, lane_ok, pb, pc, pend);
-				if (t + 2 < tiles)
-					v3_visit<CS, 2>(P, w, ph, t + 2, tiles, n_fast, lane_ok, pc, pa, pend);
+			if (V3::kStages == 3) {
+				for (uint32_t t = 0; t < tiles; t += 3) { // sass-loop-v3
+					v3_visit<CS, 0>(P, w, ph, t, tiles, n_fast, lane_ok, pa, pb, pend);
+					if (t + 1 < tiles)
+						v3_visit<CS, 1>(P, w, ph, t + 1, tiles, n_fast, lane_ok, pb, pc, pend);
+					if (t + 2 < tiles)
+						v3_visit<CS, 2>(P, w, ph, t + 2, tiles, n_fast, lane_ok, pc, pa, pend);
+				}
+			} else {
+				for (uint32_t t = 0; t < tiles; t += 4) { // sass-loop-v3
+					v3_visit<CS, 0>(P, w, ph, t, tiles, n_fast, lane_ok, pa, pb, pend);
+					if (t + 1 < tiles)
+						v3_visit<CS, 1>(P, w, ph, t + 1, tiles, n_fast, lane_ok, pb, pc, pend);
+					if (t + 2 < tiles)
+						v3_visit<CS, 2>(P, w, ph, t + 2, tiles, n_fast, lane_ok, pc, pd, pend);
+					if (t + 3 < tiles)
+						v3_visit<CS, 3 % V3::kStages>(P, w, ph, t + 3, tiles, n_fast, lane_ok, pd, pa, pend);
+				}
 			}
 			v3_resolve(pend);
 			v3_pend_clear(pend);
@@ -778,7 +839,7 @@ __global__ void __launch_bounds__(V3::kThreads, 1)
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
 	// zero the bins (all threads), set up the ring
-	for (int i = tid; i < (kVsWords + 2 * kWaveWords) / 4; i += V3::kThreads)
+	for (int i = tid; i < (V3::kVsOff + V3::kVsTableWords * 4) / 16; i += V3::kThreads)
 		reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
 #ifdef SCOPE_V3_NOLOAD
 	for (int i = tid; i < V3::kStages * V3::kTileBytes / 4; i += V3::kThreads)

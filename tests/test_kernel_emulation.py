@@ -369,13 +369,14 @@ def test_v3_extreme_geometries(emul_libs, oracle, pkg):
 
 
 def test_v3_emulator_catches_injected_bugs(oracle, pkg, tmp_path):
-    """one deliberate bug each in a copy of scope_fused_v3.cuh: the flush's division by 260 off by one in its magic
-    number, the vectorscope index bias for V - 16 missing, one arrival too few on the "empty" barriers"""
+    """one deliberate bug each in a copy of scope_fused_v3.cuh: the flush's division by 132 with a wrong magic number,
+    the wrong bit of U selecting a word's half, one arrival too few on the "empty" barriers"""
     import shutil
     csrc = os.path.join(ROOT, "obs-color-monitor_b200", "csrc")
     bugs = {
-        "div260": ("const uint32_t vq = ((idx >> 2) * 64528u) >> 22;", "const uint32_t vq = ((idx >> 2) * 64000u) >> 22;"),
-        "vbias": ("constexpr uint32_t kV3UBias = 65536u - V3::kVStride * V3::kVMin;", "constexpr uint32_t kV3UBias = 65536u - V3::kVStride * (V3::kVMin - 1);"),
+        "div132": ("const uint32_t v = ((w >> 2) * 1986u) >> 16;", "const uint32_t v = ((w >> 2) * 1900u) >> 16;"),
+        "half": ("const F2 t = f2_fma(f2_pack(idx & 0xFFFFu, ru & 0x80u), k.vs_mul, k.vs_add);",
+                 "const F2 t = f2_fma(f2_pack(idx & 0xFFFFu, ru & 0x40u), k.vs_mul, k.vs_add);"),
         "arrivals": ("mbar_init(bar_empty + 8 * s, V3::kWarps);", "mbar_init(bar_empty + 8 * s, V3::kWarps - 1);"),
     }
     frames = small_batch(pkg)

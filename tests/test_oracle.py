@@ -229,3 +229,15 @@ def test_device_side_generators_match_frames_py(pkg):
                               frames_torch.mixed_batch(1, 700, 130, cpu, first_index=seed, content="ui")[0].numpy())
     assert np.array_equal(pkg.frames.ramp(300, 77), frames_torch.mixed_batch(1, 300, 77, cpu, content="ramp")[0].numpy())
     assert np.array_equal(pkg.frames.mixed(64, 48, 6), frames_torch.mixed_batch(1, 64, 48, cpu, first_index=6, content="solid")[0].numpy())
+
+
+def test_fused_transform_ranges_the_headline_kernel_relies_on(oracle):
+    """scope_fused_kernel_v3 sizes its vectorscope table for V in [16, 240] (csrc/scope_fused_v3.cuh: words
+    132 * 16 .. 132 * 241): true for all 2^24 colours in both colour spaces, for the exact transform it evaluates"""
+    for cs in (1, 2):
+        t, clamp = oracle.rgb_to_yuv_table(cs)
+        assert not clamp
+        v = (t >> 16) & 0xFF
+        u = t & 0xFF
+        assert int(v.min()) >= 16 and int(v.max()) <= 240, (cs, int(v.min()), int(v.max()))
+        assert int(u.min()) >= 15 and int(u.max()) <= 239

@@ -180,6 +180,7 @@ extern "C" int emul_run(EmulRequest *rq)
 	P.vscope_acc = rq->vs_acc;
 	P.vscope_stride = 65536;
 	P.coef = coef_for(rq->colorspace);
+	v3_param_consts(P.v3c);
 	l.kernel = rq->kernel;
 	l.src = rq->src;
 	l.vs = rq->vscope != 0;
