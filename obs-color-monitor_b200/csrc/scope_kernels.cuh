@@ -232,7 +232,7 @@ struct StripParams {
 	int32_t colorspace;       // 1 = BT.601, else BT.709 (only the strict transform looks at it; the exact one has `coef`)
 	uint32_t v3c[8];          // scope_fused_kernel_v3: its float / integer constants as LAUNCH PARAMETERS (v3_param_consts):
 	                          // ptxas re-materialised them as immediates with ~18 MOVs per visit (10 % of all executed
-	                          // instructions, profiles/ncu_lines_r02d.md); from the constant bank they are free operands
+	                          // instructions, profiles/ncu_lines_r02e.md); from the constant bank they are free operands
 	uint32_t rt_zero;         // always 0, but only known at run time: the consumers AND it with the pixels they loaded
 	                          // and add it to the address of the "stage is free" arrive, so that ptxas must keep the
 	                          // arrive behind the arrival of the data (a `mov 0` inside inline PTX is folded by ptxas)
