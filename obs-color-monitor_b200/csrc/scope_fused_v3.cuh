@@ -34,10 +34,10 @@ namespace scope {
 #define SCOPE_V3 1 // 0: the general kernel serves the headline combination as well (A/B builds)
 #endif
 #ifndef SCOPE_V3_WARPS
-#define SCOPE_V3_WARPS 23
+#define SCOPE_V3_WARPS 27
 #endif
 #ifndef SCOPE_V3_STAGES
-#define SCOPE_V3_STAGES 4
+#define SCOPE_V3_STAGES 3
 #endif
 #ifndef SCOPE_V3_L2_AHEAD
 #define SCOPE_V3_L2_AHEAD 6 // tiles the producer's L2 prefetch runs ahead of its loads (0: none)
