@@ -52,6 +52,9 @@ def parse_args():
                     help="batch = the headline (BASELINE config 5 / metric); roi-tiled-8k = config 4; "
                          "stream-vscope-4k = config 3")
     ap.add_argument("--bands", default="rows", choices=["rows", "cols"])
+    ap.add_argument("--in-flight", type=int, default=2, help="roi-tiled-8k: frames in flight (streams, accumulator sets)")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="roi-tiled-8k on ONE GPU: do rank 0's share of an M-rank run (a rank's pipeline without M GPUs)")
     ap.add_argument("--graph", action="store_true",
                     help="roi-tiled-8k: replay each frame's launches (reset, accumulate, cross-rank step) as one CUDA graph, "
                          "so that the number is the device's and not the Python harness's (not with --reduce nccl at N > 1)")
@@ -282,8 +285,10 @@ def run_config4_record(args, eng, pkg, dev, world, rank):
     for bands, red in plans:
         for attempt in (red, "nccl"):
             try:
-                r = measure_config4(eng, pkg, dev, world, rank, bands=bands, reduce=attempt, graph=True, steps=200,
-                                    warmup=20, colorspace=args.colorspace)
+                # column bands at N ranks: 240 / N strips = CTAs per frame and rank; eight frames in flight fill the GPU
+                r = measure_config4(eng, pkg, dev, world, rank, bands=bands, reduce=attempt, graph=True,
+                                    steps=400 if world > 1 else 200, warmup=24, colorspace=args.colorspace,
+                                    in_flight=(8 if bands == "cols" else 4) if world > 1 else 2)
                 err = None
             except Exception as e:
                 r, err = None, repr(e)[:300]
@@ -304,7 +309,7 @@ def run_config4_record(args, eng, pkg, dev, world, rank):
     best = max((v for k, v in rec.items() if isinstance(v, dict) and "value" in v), key=lambda v: v["value"], default=None)
     if best is not None:
         rec["best"] = {"bands": best["bands"], "reduce": best["reduce"], "value": best["value"],
-                       "ms_per_frame": best["ms_per_frame"]}
+                       "ms_per_frame": best["ms_per_frame"], "frames_in_flight": best["frames_in_flight"]}
     return rec
 
 
@@ -697,7 +702,7 @@ def run_e2e(args, eng, st, batch, dev, world, rank):
 
 
 def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", graph=True, steps=200, warmup=20,
-                    colorspace=2, check=True):
+                    colorspace=2, check=True, in_flight=2, emulate_world=0):
     """BASELINE config 4: ONE 7680x4320 frame, waveform of luma (components 0x20), split into row bands (or
     column bands) over the ranks.  A step = one frame; two frames are in flight on two streams (double-buffered
     accumulators and images), so the cross-rank step of frame i overlaps the accumulation of frame i + 1.
@@ -708,6 +713,12 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
             -> barrier
       cols  a rank's columns are final: its strip kernel stores them as u8 straight into every rank's image (peer
             stores; nccl: all-gather of the u8 bands) -> one barrier.  No reduce step at all.
+    in_flight = F: F frames are in flight on F streams (F sets of accumulators and images).  A rank's band of a
+    frame is at most 240 / N strips = CTAs of the strip kernel, far fewer than the GPU holds at N = 4: only several
+    frames in flight fill it, which is what a stream of video frames offers anyway (the per-frame latency is reported
+    next to the rate).
+    emulate_world = M (one process, one GPU): this GPU does rank 0's share of an M-rank run - the same band kernel,
+    the same number of launches, no peers - to see a rank's pipeline without paying for M GPUs.
     Returns a dict (every rank computes it; rank 0 reports)."""
     import torch
     import torch.distributed as dist
@@ -715,15 +726,20 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
     from obs_color_monitor_b200 import frames_torch
 
     W, H = 7680, 4320
+    F = max(1, int(in_flight))
+    emulate = int(emulate_world) if world == 1 and emulate_world and emulate_world > 1 else 0
     st = pkg.ScopeSettings(scopes=pkg.SCOPE_WAVE, wave_components=pkg.COMP_Y, colorspace=colorspace)
 
     def new_tiled():
         if reduce == "nccl":
             return pkg.sharding.TiledFrame(eng, W, H, st, mode=bands)
-        return pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=bands, two_shot=reduce in ("peers", "nvls"),
-                                           nvls=reduce.startswith("nvls"))
+        tf = pkg.sharding.PeerTiledFrame(eng, W, H, st, mode=bands, two_shot=reduce in ("peers", "nvls"),
+                                         nvls=reduce.startswith("nvls"))
+        if emulate:
+            tf.bands = (pkg.sharding.row_bands(H, emulate) if bands == "rows" else pkg.sharding.col_bands(W, emulate))[:1]
+        return tf
 
-    ring = [new_tiled(), new_tiled()]
+    ring = [new_tiled() for _ in range(F)]
     a, b = ring[0].my_band
     # 4 different frames so that successive steps do not hit L2 (an 8K frame is 133 MB > L2; a rank's band of 4
     # frames is 133 MB at N = 4)
@@ -734,7 +750,8 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         full = [frames_torch.mixed_batch(1, W, H, dev, first_index=4 * i + 3, content="natural")[0] for i in range(4)]
         data = [torch.as_strided(f.reshape(-1)[a * 4:], (H, (W - a) * 4), (W * 4, 1)) for f in full]
         width = b - a
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(F)]
+    check = check and not emulate
 
     def enqueue(j, k):
         tf = ring[j]
@@ -750,16 +767,17 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         torch.cuda.synchronize()
 
     outs = {}
-    for i in range(max(warmup, 4)):
-        with torch.cuda.stream(streams[i % 2]):
-            outs[i % 2] = enqueue(i % 2, i % 4)
+    n_warm = (max(warmup, 4) + F - 1) // F * F
+    for i in range(n_warm):
+        with torch.cuda.stream(streams[i % F]):
+            outs[i % F] = enqueue(i % F, i % 4)
     barrier()
     parity = None
     if check:
         # the last two frames against the unsharded pass on this GPU (which tests/ pins on the oracle at 8K)
         bad = 0
-        for j, i in ((0, max(warmup, 4) - 2), (1, max(warmup, 4) - 1)):
-            j, k = i % 2, i % 4
+        for i in (n_warm - 2, n_warm - 1) if F > 1 else (n_warm - 1,):
+            j, k = i % F, i % 4
             if bands == "rows":
                 whole_src = frames_torch.mixed_batch(1, W, H, dev, first_index=4 * k + 3, content="natural") \
                     if world == 1 else None
@@ -769,25 +787,29 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
                 ref = eng.accumulate_device(whole_src, settings=st)
                 torch.cuda.synchronize()
                 bad += int(not torch.equal(outs[j]["wave"][0], ref["wave"][0]))
-        parity = {"checked_frames": 2 if (bands == "cols" or world == 1) else 0, "mismatches": bad}
+        parity = {"checked_frames": min(F, 2) if (bands == "cols" or world == 1) else 0, "mismatches": bad}
     launches_per_frame, big = None, None
     use_graph = graph and not (reduce == "nccl" and world > 1)
     graph_error = None
-    G = 8    # frames per graph replay: both streams inside ONE graph (fork / join), so that the host's graph-launch
-             # rate (a few tens of microseconds per replay from Python) cannot be what a 20-microsecond frame waits for
+    G = max(8, 2 * F) // F * F   # frames per graph replay: all streams inside ONE graph (fork / join), so that the host's
+             # graph-launch rate (a few tens of microseconds per replay from Python) cannot be what a 20-microsecond
+             # frame waits for
     if use_graph:
         try:
             big = torch.cuda.CUDAGraph()
             l_before = eng.launch_count
-            fork, joined = torch.cuda.Event(), torch.cuda.Event()
+            fork, graph_events = torch.cuda.Event(), []
             with torch.cuda.graph(big, stream=streams[0]):
                 fork.record(streams[0])
-                streams[1].wait_event(fork)
+                for s_ in streams[1:]:
+                    s_.wait_event(fork)
                 for i in range(G):
-                    with torch.cuda.stream(streams[i % 2]):
-                        enqueue(i % 2, i % 4)
-                joined.record(streams[1])
-                streams[0].wait_event(joined)
+                    with torch.cuda.stream(streams[i % F]):
+                        enqueue(i % F, i % 4)
+                for s_ in streams[1:]:
+                    graph_events.append(torch.cuda.Event())
+                    graph_events[-1].record(s_)
+                    streams[0].wait_event(graph_events[-1])
             launches_per_frame = (eng.launch_count - l_before) / G
             for _ in range(2):
                 with torch.cuda.stream(streams[0]):
@@ -809,8 +831,8 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
                 with torch.cuda.stream(streams[0]):
                     big.replay()
             return
-        with torch.cuda.stream(streams[i % 2]):
-            enqueue(i % 2, i % 4)
+        with torch.cuda.stream(streams[i % F]):
+            enqueue(i % F, i % 4)
 
     # the accumulation kernel alone (this rank's band, stream 0, events around single launches): what the frame time
     # is made of besides it is the cross-rank step and whatever the two streams do not overlap
@@ -838,8 +860,10 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         s_.wait_event(ev0)
     for i in range(steps):
         step(i)
-    join.record(streams[1])
-    streams[0].wait_event(join)
+    for s_ in streams[1:]:
+        join = torch.cuda.Event()
+        join.record(s_)
+        streams[0].wait_event(join)
     ev1.record(streams[0])
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -862,9 +886,10 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         "metric": "frames/sec ROI-tiled waveform (luma) @7680x4320 BGRA", "value": steps / (ms * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": steps, "warmup": max(warmup, 4), "ms_per_frame": ms / steps, "bands": bands,
         "reduce": reduce if world > 1 else "none (one rank)", "graph": bool(use_graph), "graph_error": graph_error,
-        "frames_in_flight": 2, "frames_per_graph": G if use_graph else None,
+        "frames_in_flight": F, "frames_per_graph": G if use_graph else None, "emulated_world": emulate or None,
+        "frame_latency_us": 1e3 * F * ms / steps,   # Little's law: F frames in flight at this rate
         "band_kernel_us": kernel_us,
-        "band_bytes": W * H * 4 // world,
+        "band_bytes": W * H * 4 // (emulate or world),
         "bytes_over_nvlink_per_rank_per_frame": int(nvlink),
         "gpu_launches_per_frame": launches_per_frame if launches_per_frame is not None else (eng.launch_count - l0) / steps,
         "achieved_read_GBps_all_ranks": steps * W * H * 4 / (ms * 1e-3) / 1e9, "clocks": clocks, "parity": parity,
@@ -889,7 +914,8 @@ def run_roi_tiled(args):
         dist.init_process_group("nccl", device_id=dev)
     eng = pkg.ScopeEngine(local_rank)
     res = measure_config4(eng, pkg, dev, world, rank, bands=args.bands, reduce=args.reduce, graph=args.graph,
-                          steps=args.steps, warmup=args.warmup, colorspace=args.colorspace)
+                          steps=args.steps, warmup=args.warmup, colorspace=args.colorspace, in_flight=args.in_flight,
+                          emulate_world=args.emulate_world)
     if rank == 0:
         peak = _hbm_peak()[0]
         res["roofline"].update({"peak": peak, "frac": res["roofline"]["achieved"] / peak})

@@ -82,7 +82,8 @@ struct scope_ctx {
 	};
 	std::vector<KernelFacts> kernel_facts;
 	// work counters of the dynamically scheduled launches (one slot per launch, round robin)
-	uint32_t *d_counters = nullptr;
+	static constexpr uint32_t kCounterPool = 16384;
+	uint32_t *d_counters = nullptr; // pool of kCounterPool counters, handed out in slices, round robin
 	uint32_t counter_next = 0;
 	RingSlot ring[SCOPE_RING_SLOTS];
 	std::mutex mu;
@@ -399,9 +400,16 @@ int launch_strip(scope_ctx *ctx, const Request &rq, cudaStream_t stream)
 		uint32_t ch = P.items / (grid * 6u);
 		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
 		if (!ctx->d_counters)
-			CU_TRY(ctx, cudaMalloc(&ctx->d_counters, 256 * sizeof(uint32_t)));
-		P.chunk_counter = ctx->d_counters + (ctx->counter_next++ & 255u);
-		CU_TRY(ctx, cudaMemsetAsync(P.chunk_counter, 0, sizeof(uint32_t), stream));
+			CU_TRY(ctx, cudaMalloc(&ctx->d_counters, ctx->kCounterPool * sizeof(uint32_t)));
+		// the headline kernel claims strips frame by frame (one counter per frame): a CTA then changes frames - and
+		// flushes its vectorscope table - a few times per launch instead of after nearly every chunk
+		const uint32_t n_counters = (v3 && SCOPE_V3_FRAME_AFFINE && rq.n_frames <= ctx->kCounterPool / 4u) ? rq.n_frames : 1u;
+		P.frame_affine = n_counters == rq.n_frames && v3 && SCOPE_V3_FRAME_AFFINE ? 1u : 0u;
+		if (ctx->counter_next + n_counters > ctx->kCounterPool)
+			ctx->counter_next = 0; // (a slice is reused only after kCounterPool counters' worth of later launches)
+		P.chunk_counter = ctx->d_counters + ctx->counter_next;
+		ctx->counter_next += n_counters;
+		CU_TRY(ctx, cudaMemsetAsync(P.chunk_counter, 0, n_counters * sizeof(uint32_t), stream));
 		P.items_per_cta = 0;
 	} else {
 		P.items_per_cta = (P.items + grid - 1) / grid;

@@ -48,6 +48,25 @@ namespace scope {
 #ifndef SCOPE_V3_FFMA2
 #define SCOPE_V3_FFMA2 1 // 0: scalar FFMA / FADD (A/B partner)
 #endif
+#ifndef SCOPE_V3_RESOLVE_NOW
+#define SCOPE_V3_RESOLVE_NOW 1 // the ordinary block issues its vectorscope adds FIRST and looks at their old values at its own
+                               // end, behind the twelve column-bin adds (0: the look is deferred to the next visit, which
+                               // keeps twelve registers alive across the visit boundary)
+#endif
+#ifndef SCOPE_V3_SMEM_CONSTS
+#define SCOPE_V3_SMEM_CONSTS 1 // the per-visit constants that must sit in registers (IMAD addends, PRMT carrier, f32x2 addends) are
+                               // read ONCE per thread from a shared-memory copy: ptxas re-materialises anything it can trace
+                               // to the constant bank with an LDC per visit (nine of them), a loaded value it has to keep
+#endif
+#ifndef SCOPE_V3_WIDE_EMIT
+#define SCOPE_V3_WIDE_EMIT 1 // end of a full strip: 16-byte loads / stores, four levels per warp and step (0: one level per step)
+#endif
+#ifndef SCOPE_V3_FRAME_AFFINE
+#define SCOPE_V3_FRAME_AFFINE 1 // strips are claimed frame by frame (StripParams::frame_affine; 0: one counter over the batch)
+#endif
+#ifndef SCOPE_V3_LEAN
+#define SCOPE_V3_LEAN 1 // visits that lie inside the frame and have a successor run without the per-visit checks (0: A/B partner)
+#endif
 
 struct V3 {
 	static constexpr int kWarps = SCOPE_V3_WARPS; // consumer warps; + 1 producer warp
@@ -70,7 +89,8 @@ struct V3 {
 	static constexpr int kStageOff = (kVsOff + kVsTableWords * 4 + 127) / 128 * 128;
 	static constexpr int kBarOff = kStageOff + kStages * kTileBytes;
 	static constexpr int kQueueOff = kBarOff + 2 * 8 * kStages + 16;
-	static constexpr int kTotal = kQueueOff + kQueue * 8 + 16;
+	static constexpr int kConstOff = kQueueOff + kQueue * 8 + 16; // 16 words: SCOPE_V3_SMEM_CONSTS
+	static constexpr int kTotal = kConstOff + 64;
 	static_assert(kTotal <= 227 * 1024, "shared memory");
 #ifndef SCOPE_EMULATE // (the emulation tests build a copy with a one-entry mailbox on purpose)
 	static_assert(kStages <= kQueue, "chunk mailbox shorter than the ring");
@@ -414,6 +434,69 @@ __device__ __forceinline__ void v3_block_fast(const uint32_t (&p)[4], const V3Co
 	}
 }
 
+// the same block with the vectorscope adds in front: their old values have arrived by the time the column-bin adds
+// have been issued, so the take-back needs no state that outlives the block
+template <int CS>
+__device__ __forceinline__ void v3_block_fast_now(const uint32_t (&p)[4], const V3Consts &k, uint32_t ku, uint32_t kv,
+						  uint32_t zero_reg)
+{
+	V3Px px[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		px[i] = v3_bytes(p[i], zero_reg);
+	V3Pend q;
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		v3_vs_target(v3_uv<CS>(px[i].cb, px[i].cg, px[i].cr, k, ku, kv), k, q.addr[i], q.add[i]);
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		if (SCOPE_V3_SKIP & 2) {
+			v3_keep(q.addr[i], q.add[i]);
+			q.old[i] = 0;
+		} else {
+			q.old[i] = atom_shared_add(q.addr[i], q.add[i]);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i += 2) {
+		uint32_t a0, a1;
+		f2_unpack(f2_fma(f2_pack(px[i].cb, px[i + 1].cb), k.k128, k.wb0), a0, a1);
+		if (SCOPE_V3_SKIP & 1) {
+			v3_keep(a0, a1);
+		} else {
+			red_shared(a0, 1u);
+			red_shared(a1, 1u);
+		}
+		f2_unpack(f2_fma(f2_pack(px[i].cg, px[i + 1].cg), k.k128, k.wb0), a0, a1);
+		if (SCOPE_V3_SKIP & 1) {
+			v3_keep(a0, a1);
+		} else {
+			red_shared(a0, 0x10000u);
+			red_shared(a1, 0x10000u);
+		}
+		f2_unpack(f2_fma(f2_pack(px[i].cr, px[i + 1].cr), k.k128, k.wb1), a0, a1);
+		if (SCOPE_V3_SKIP & 1) {
+			v3_keep(a0, a1);
+		} else {
+			red_shared(a0, 1u);
+			red_shared(a1, 1u);
+		}
+	}
+	v3_resolve(q);
+}
+
+template <int CS>
+__device__ __forceinline__ void v3_block_ordinary(const uint32_t (&p)[4], const V3Consts &k, uint32_t ku, uint32_t kv,
+						  uint32_t zero_reg, V3Pend &q)
+{
+#if SCOPE_V3_RESOLVE_NOW
+	(void)q;
+	v3_block_fast_now<CS>(p, k, ku, kv, zero_reg);
+#else
+	v3_block_fast<CS>(p, k, ku, kv, zero_reg, q);
+#endif
+}
+
 // all 4 x 32 pixel words equal (solid regions, letterbox bars): 32 lanes on one vectorscope word would take 32
 // cycles per add; here lane 0 adds 128 at once.  The column bins have no such problem (lane = column = bank).
 template <int CS>
@@ -564,6 +647,65 @@ __device__ __forceinline__ void v3_emit_strip(const StripParams &P, uint32_t *wa
 	workers_bar<NW>();
 }
 
+// The same for a strip whose 32 columns all lie inside the frame and whose output rows can be written 16 bytes at a
+// time: a lane takes FOUR neighbouring columns of one level (one 16-byte load per plane, conflict-free: eight lanes
+// cover a level's 128 bytes), a warp four levels per step - 64 steps per strip instead of 256, and an empty group of
+// four levels costs two loads, a vote and one store.  The level's histogram share is summed over the lane's four
+// columns first (B and G still packed: 4 x height <= 65 535, checked by the caller) and then over the eight lanes of
+// the level by three butterfly steps.
+__device__ __forceinline__ void v3_emit_strip_wide(const StripParams &P, uint32_t *wave0, uint32_t frame, uint32_t x_strip,
+						   int warp, int lane)
+{
+	constexpr int NW = V3::kWarps;
+	workers_bar<NW>();
+	uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
+	const bool do_hist = P.hist_mask != 0u;
+	const int sub = lane >> 3, quad = lane & 7; // level inside the group of four; which four columns
+	uint4 *w4 = reinterpret_cast<uint4 *>(wave0);
+	uint32_t *img = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride) + (P.x_offset + x_strip) + 4 * quad;
+	for (int g = warp; g < 64; g += NW) {
+		const int v = 4 * g + sub;
+		const int idx = v * 8 + quad;
+		const uint4 a = w4[idx], b = w4[kWaveWords / 4 + idx];
+		uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)(255 - v) * P.out_width);
+		const uint32_t any = (a.x | a.y | a.z | a.w) | (b.x | b.y | b.z | b.w);
+		if (!__any_sync(0xFFFFFFFFu, any != 0u)) {
+			*dst = make_uint4(0, 0, 0, 0);
+			continue;
+		}
+		w4[idx] = make_uint4(0, 0, 0, 0);
+		w4[kWaveWords / 4 + idx] = make_uint4(0, 0, 0, 0);
+		uint4 o; // bytes B, G, R, 0 per column
+		o.x = __byte_perm(min_u16x2(a.x, 0x00FF00FFu), min(b.x, 255u), 0x5420);
+		o.y = __byte_perm(min_u16x2(a.y, 0x00FF00FFu), min(b.y, 255u), 0x5420);
+		o.z = __byte_perm(min_u16x2(a.z, 0x00FF00FFu), min(b.z, 255u), 0x5420);
+		o.w = __byte_perm(min_u16x2(a.w, 0x00FF00FFu), min(b.w, 255u), 0x5420);
+		*dst = o;
+		if (do_hist) {
+			uint32_t bg = (a.x + a.y) + (a.z + a.w); // two u16 sums side by side
+			uint32_t sr = (b.x + b.y) + (b.z + b.w);
+			bg += __shfl_xor_sync(0xFFFFFFFFu, bg, 1); // (8 x height <= 65 535 as well)
+			sr += __shfl_xor_sync(0xFFFFFFFFu, sr, 1);
+			uint32_t sb = bg & 0xFFFFu, sg = bg >> 16;
+#pragma unroll
+			for (int m = 2; m <= 4; m += 2) {
+				sb += __shfl_xor_sync(0xFFFFFFFFu, sb, m);
+				sg += __shfl_xor_sync(0xFFFFFFFFu, sg, m);
+				sr += __shfl_xor_sync(0xFFFFFFFFu, sr, m);
+			}
+			if (quad == 0) {
+				if (sr)
+					atomicAdd(hist + v * 4 + 0, sr);
+				if (sg)
+					atomicAdd(hist + v * 4 + 1, sg);
+				if (sb)
+					atomicAdd(hist + v * 4 + 2, sb);
+			}
+		}
+	}
+	workers_bar<NW>();
+}
+
 // ---------------------------------------------------------------------------
 // The ring.  Tile t of EVERY strip goes to stage t mod kStages (a strip restarts at stage 0), so that the consumers'
 // loop, unrolled kStages times, knows its stage at compile time: barrier and tile addresses are immediates and
@@ -580,14 +722,43 @@ __device__ __forceinline__ void v3_produce(const StripParams &P, const CUtensorM
 	const uint32_t tiles = (P.height + V3::kTileRows - 1) / V3::kTileRows;
 	uint32_t phases = 0; // bit s: phase of stage s
 	uint32_t qw = 0;
+	// frame-affine claiming: this CTA's home frame, how many CTAs share a frame, frames found used up so far
+	const uint32_t n_frames = P.items / P.strips;
+	uint32_t cur_f = (uint32_t)(((unsigned long long)blockIdx.x * n_frames) / gridDim.x), used_up = 0;
+	const uint32_t share = gridDim.x / n_frames + 2u;
 	for (;;) {
-		// guided self-scheduling (see tma_produce)
-		const uint32_t seen = *reinterpret_cast<volatile const uint32_t *>(P.chunk_counter);
-		uint32_t want = seen < P.items ? (P.items - seen) / (2u * gridDim.x) : 1u;
-		want = min(max(want, 1u), P.chunk_items);
-		const uint32_t first = atomicAdd(P.chunk_counter, want);
-		const bool done = first >= P.items;
-		const uint32_t last = min(first + want, P.items);
+		uint32_t first, last;
+		bool done;
+		if (P.frame_affine) {
+			// strips of the frame this CTA is on, as long as there are any (guided: 1 / (2 x share) of what the
+			// frame has left, at most chunk_items); then the next frame that still has strips.  A frame that was
+			// found used up stays used up, so after n_frames of them in a row the batch is done.
+			done = true;
+			first = last = 0;
+			while (used_up < n_frames) {
+				const uint32_t seen = *reinterpret_cast<volatile const uint32_t *>(P.chunk_counter + cur_f);
+				if (seen < P.strips) {
+					const uint32_t want = min(max((P.strips - seen) / (2u * share), 1u), P.chunk_items);
+					const uint32_t got = atomicAdd(P.chunk_counter + cur_f, want);
+					if (got < P.strips) {
+						first = cur_f * P.strips + got;
+						last = cur_f * P.strips + min(got + want, P.strips);
+						done = false;
+						break;
+					}
+				}
+				cur_f = cur_f + 1u == n_frames ? 0u : cur_f + 1u;
+				used_up++;
+			}
+		} else {
+			// guided self-scheduling over the whole batch (see tma_produce)
+			const uint32_t seen = *reinterpret_cast<volatile const uint32_t *>(P.chunk_counter);
+			uint32_t want = seen < P.items ? (P.items - seen) / (2u * gridDim.x) : 1u;
+			want = min(max(want, 1u), P.chunk_items);
+			first = atomicAdd(P.chunk_counter, want);
+			done = first >= P.items;
+			last = min(first + want, P.items);
+		}
 		// announce the chunk (or the end) before its first tile (stage 0) can complete
 		mbar_wait(bar_empty, (phases & 1u) ^ 1u);
 		chunk_q[2 * (qw % kQueue)] = first;
@@ -642,6 +813,7 @@ struct V3Warp {
 	V3Consts k;
 	uint32_t ku, kv, zero;
 	uint32_t rows_base; // this lane's ldmatrix address inside stage 0
+	uint32_t base;      // the CTA's shared-memory window
 	uint32_t bar_full, bar_empty;
 	uint32_t y_warp;
 	int lane;
@@ -704,7 +876,7 @@ __device__ __forceinline__ void v3_visit(const StripParams &P, const V3Warp &w, 
 	// and no lane whose four words are equal (a flat block needs every lane like that)
 	const bool special = m_and <= 0x00FFFFFFu || m_and == m_or;
 	if (t < n_fast && !__any_sync(0xFFFFFFFFu, special)) {
-		v3_block_fast<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+		v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
 	} else {
 		// sass-cold{
 		bool done = false;
@@ -713,7 +885,7 @@ __device__ __forceinline__ void v3_visit(const StripParams &P, const V3Warp &w, 
 			if (__all_sync(0xFFFFFFFFu, ((m_and ^ m_or) | (p[0] ^ p_lane0)) == 0u))
 				v3_block_flat<CS>(p[0], w.k, w.ku, w.kv, w.zero, w.lane);
 			else
-				v3_block_fast<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+				v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
 			done = true;
 		}
 		if (!done) {
@@ -723,6 +895,66 @@ __device__ __forceinline__ void v3_visit(const StripParams &P, const V3Warp &w, 
 			for (int i = 0; i < 4; i++)
 				rows_ok |= (y0 + i < P.height ? 1u : 0u) << i;
 			v3_block_slow<CS>(p, w.k, w.ku, w.kv, w.zero, lane_ok, rows_ok);
+		}
+		// sass-cold}
+	}
+}
+
+// hand stage S back, lean form: the arrive's address register is (shared-memory base | pn[0] & 0) and the barrier's
+// offset an immediate.  ONE of ldmatrix's four destination registers is enough for the dependency: the scoreboard
+// that the arrive has to wait for belongs to the instruction, not to a register.
+template <int S>
+__device__ __forceinline__ void v3_release_lean(const V3Warp &w, uint32_t p0)
+{
+#ifndef SCOPE_V3_NOLOAD
+	if (w.lane == 0) {
+#ifdef SCOPE_EMULATE
+		mbar_arrive((w.base | (p0 & w.zero)) + V3::kBarOff + 8 * (V3::kStages + S));
+#else
+		asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(w.base | (p0 & w.zero)),
+			     "n"(V3::kBarOff + 8 * (V3::kStages + S))
+			     : "memory");
+#endif
+	}
+#endif
+}
+
+// A visit whose block lies completely inside the frame and that has a successor (t + 1 < tiles, t < n_fast): no
+// per-visit range checks, and the look at the previous visit's vectorscope adds (v3_resolve) is part of the ONE vote -
+// an old value with its top bit set is as rare as a flat block and takes the same way out.
+template <int CS, int S>
+__device__ __forceinline__ void v3_visit_lean(const V3Warp &w, V3Phase &ph, const uint32_t (&p)[4], uint32_t (&pn)[4],
+					      V3Pend &pend)
+{
+	constexpr int S1 = (S + 1) % V3::kStages;
+	v3_load<S1>(w, ph, pn, true);
+	v3_release_lean<S1>(w, pn[0]);
+	const uint32_t m_and = p[0] & p[1] & p[2] & p[3], m_or = p[0] | p[1] | p[2] | p[3];
+#if SCOPE_V3_RESOLVE_NOW
+	const uint32_t olds = 0u; // (`pend` is empty throughout: every block settles its own adds)
+#else
+	const uint32_t olds = pend.old[0] | pend.old[1] | pend.old[2] | pend.old[3];
+#endif
+#ifdef SCOPE_V3_NOP
+	if (m_and == 0x12345678u && m_or == 0x9ABCDEF0u)
+		red_shared(w.rows_base, olds);
+	return;
+#endif
+	const bool special = m_and <= 0x00FFFFFFu || m_and == m_or || (olds & 0x80008000u) != 0u;
+	if (!__any_sync(0xFFFFFFFFu, special)) {
+		v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+	} else {
+		// sass-cold{
+		v3_resolve(pend);
+		v3_pend_clear(pend);
+		if (__all_sync(0xFFFFFFFFu, m_and > 0x00FFFFFFu)) {
+			const uint32_t p_lane0 = __shfl_sync(0xFFFFFFFFu, p[0], 0);
+			if (__all_sync(0xFFFFFFFFu, ((m_and ^ m_or) | (p[0] ^ p_lane0)) == 0u))
+				v3_block_flat<CS>(p[0], w.k, w.ku, w.kv, w.zero, w.lane);
+			else
+				v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+		} else {
+			v3_block_slow<CS>(p, w.k, w.ku, w.kv, w.zero, true, 0xFu);
 		}
 		// sass-cold}
 	}
@@ -751,7 +983,21 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 	w.kv = coef.kv;
 #endif
 	w.zero = P.rt_zero; // 0, known only at run time (see StripParams)
+#if SCOPE_V3_SMEM_CONSTS
+	{
+		// (written by thread 0 before the CTA's first barrier, see the kernel)
+		const volatile uint32_t *kc = reinterpret_cast<const volatile uint32_t *>(smem + V3::kConstOff);
+		w.ku = kc[0];
+		w.kv = kc[1];
+		w.zero = kc[2];
+		w.k.round = f2_pack(kc[3], kc[4]);
+		w.k.k128 = f2_pack(kc[5], kc[5]);
+		w.k.exp_hi = kc[6];
+		w.k.vs_add = f2_pack(kc[7], kc[8]);
+	}
+#endif
 	w.rows_base = smem_base + V3::kStageOff + (uint32_t)warp * (V3::kRows * kStripPx * 4) + (uint32_t)lane * 16u;
+	w.base = smem_base;
 	w.bar_full = bar_full;
 	w.bar_empty = bar_empty;
 	w.y_warp = (uint32_t)warp * V3::kRows;
@@ -799,8 +1045,20 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 			// tile 0 (the chunk announcement already waited for the first item's)
 			v3_load<0>(w, ph, pa, item != first);
 			v3_release<0>(w, pa);
+			uint32_t t = 0;
+#if SCOPE_V3_LEAN
+			// visits [0, n_lean): inside the frame and with a successor
+			const uint32_t n_lean = min(n_fast, tiles - 1u);
+#endif
 			if (V3::kStages == 3) {
-				for (uint32_t t = 0; t < tiles; t += 3) { // sass-loop-v3
+#if SCOPE_V3_LEAN
+				for (; t + 3 <= n_lean; t += 3) { // sass-loop-v3
+					v3_visit_lean<CS, 0>(w, ph, pa, pb, pend);
+					v3_visit_lean<CS, 1>(w, ph, pb, pc, pend);
+					v3_visit_lean<CS, 2>(w, ph, pc, pa, pend);
+				}
+#endif
+				for (; t < tiles; t += 3) {
 					v3_visit<CS, 0>(P, w, ph, t, tiles, n_fast, lane_ok, pa, pb, pend);
 					if (t + 1 < tiles)
 						v3_visit<CS, 1>(P, w, ph, t + 1, tiles, n_fast, lane_ok, pb, pc, pend);
@@ -808,7 +1066,15 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 						v3_visit<CS, 2>(P, w, ph, t + 2, tiles, n_fast, lane_ok, pc, pa, pend);
 				}
 			} else {
-				for (uint32_t t = 0; t < tiles; t += 4) { // sass-loop-v3
+#if SCOPE_V3_LEAN
+				for (; t + 4 <= n_lean; t += 4) { // sass-loop-v3
+					v3_visit_lean<CS, 0>(w, ph, pa, pb, pend);
+					v3_visit_lean<CS, 1>(w, ph, pb, pc, pend);
+					v3_visit_lean<CS, 2>(w, ph, pc, pd, pend);
+					v3_visit_lean<CS, 3 % V3::kStages>(w, ph, pd, pa, pend);
+				}
+#endif
+				for (; t < tiles; t += 4) {
 					v3_visit<CS, 0>(P, w, ph, t, tiles, n_fast, lane_ok, pa, pb, pend);
 					if (t + 1 < tiles)
 						v3_visit<CS, 1>(P, w, ph, t + 1, tiles, n_fast, lane_ok, pb, pc, pend);
@@ -820,7 +1086,16 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 			}
 			v3_resolve(pend);
 			v3_pend_clear(pend);
-			v3_emit_strip(P, wave0, frame, x, lane_ok, warp, lane);
+#if SCOPE_V3_WIDE_EMIT
+			// (from the launch parameters alone, every time: nothing to keep in a register across the strip)
+			// 16-byte stores into the waveform rows, packed u16 sums of eight columns
+			const bool wide_ok = ((P.x_offset | P.out_width) & 3u) == 0u && (P.wave_stride & 15u) == 0u &&
+					     (reinterpret_cast<uintptr_t>(P.wave) & 15u) == 0u && P.height <= 8191u;
+			if (wide_ok && strip * kStripPx + kStripPx <= P.width)
+				v3_emit_strip_wide(P, wave0, frame, strip * kStripPx, warp, lane);
+			else
+#endif
+				v3_emit_strip(P, wave0, frame, x, lane_ok, warp, lane);
 		}
 	}
 	if (cur_frame != 0xFFFFFFFFu)
@@ -846,6 +1121,31 @@ __global__ void __launch_bounds__(V3::kThreads, 1)
 		reinterpret_cast<uint32_t *>(smem + V3::kStageOff)[i] = ((uint32_t)i * 2654435761u + blockIdx.x * 40503u) | 0xFF000000u;
 #endif
 	if (tid == 0) {
+#if SCOPE_V3_SMEM_CONSTS
+		{
+			volatile uint32_t *kc = reinterpret_cast<volatile uint32_t *>(smem + V3::kConstOff);
+#if SCOPE_V3_PARAM_CONSTS
+			const V3Consts k0 = v3_consts_from(P.v3c, smem_base, 0);
+			kc[0] = P.coef.ku;
+			kc[1] = P.coef.kv;
+#else
+			const V3Consts k0 = v3_consts(smem_base, 0);
+			kc[0] = v3_coef<CS>().ku;
+			kc[1] = v3_coef<CS>().kv;
+#endif
+			uint32_t lo, hi;
+			kc[2] = P.rt_zero;
+			f2_unpack(k0.round, lo, hi);
+			kc[3] = lo;
+			kc[4] = hi;
+			f2_unpack(k0.k128, lo, hi);
+			kc[5] = lo;
+			kc[6] = k0.exp_hi;
+			f2_unpack(k0.vs_add, lo, hi);
+			kc[7] = lo;
+			kc[8] = hi;
+		}
+#endif
 		for (int s = 0; s < V3::kStages; s++) {
 			mbar_init(bar_full + 8 * s, 1);
 			mbar_init(bar_empty + 8 * s, V3::kWarps);

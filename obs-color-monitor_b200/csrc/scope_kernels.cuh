@@ -217,6 +217,10 @@ struct StripParams {
 	uint32_t tma_x0_rgb, tma_x0_yuv; // TMA kernels: pixel column of the plane's first pixel inside its tensor map
 	                                 // (the map starts at the plane pointer rounded down to 16 bytes)
 	uint32_t *chunk_counter;  // global work counter of this launch (zeroed by the host)
+	uint32_t frame_affine;    // scope_fused_kernel_v3: chunk_counter points at ONE COUNTER PER FRAME (all zeroed by the host) and a
+	                          // CTA keeps claiming strips of the frame it is on until that frame is used up: the vectorscope
+	                          // table is flushed when the frame changes, and with one counter for the whole batch that is
+	                          // after nearly every chunk (0: one counter over all strips of the batch)
 	uint32_t *hist;           // [n][1024] u32, zeroed
 	uint8_t *wave;            // [n][256][out_width][4]
 	uint32_t *wave_pairs;     // partial: [2][256][out_width]: plane 0 = (B|U : lo16, G|Y : hi16), plane 1 = R|V

@@ -333,6 +333,14 @@ def test_v3_headline_batch(emul_libs, oracle, pkg):
             check(oracle, frames, out, yuv, 0x07, 0x07, True, f"v3 cs {cs} seed {seed}")
     out = run(lib, frames, kernel=K_V3, hist_comp=0, seed=9)              # waveform + vectorscope, no histogram
     check(oracle, frames, out, [oracle.rgb_to_yuv(f, 2) for f in frames], 0, 0x07, True, "v3 without histogram")
+    # tall frames: 7 tiles of 108 rows, so that the strips' first visits run through the lean loop (blocks inside the
+    # frame with a successor, no per-visit checks) - random, natural and transparent content, late and prompt loads
+    fr = pkg.frames
+    tall = np.stack([fr.random(72, 700, 13), fr.alpha_stripes(72, 700, 14), fr.natural(72, 700, 15)])   # 72: 16-byte rows, wide write-out
+    yuv = [oracle.rgb_to_yuv(f, 2) for f in tall]
+    for seed, land, ctas in ((31, 30, 2), (32, 3, 1)):
+        out = run(lib, tall, kernel=K_V3, seed=seed, land=land, ctas=ctas)
+        check(oracle, tall, out, yuv, 0x07, 0x07, True, f"v3 tall seed {seed}")
 
 
 def test_v3_saturation_flat_and_almost_flat(emul_libs, oracle, pkg):

@@ -187,6 +187,19 @@ inline uint32_t collective(Op op, uint32_t v, int src_lane = 0)
 	return w.res[b][lane][0];
 }
 
+// butterfly exchange: lane i receives the value of lane i ^ mask (full mask, uniform `mask`)
+inline uint32_t shfl_xor(uint32_t v, int mask)
+{
+	Warp &w = my_warp();
+	const int lane = my_lane(), b = w.rv.gen & 1;
+	w.vals[b][lane] = v;
+	rendezvous(w.rv, 32, [&] {
+		for (int i = 0; i < 32; i++)
+			w.res[b][i][0] = w.vals[b][(i ^ mask) & 31];
+	});
+	return w.res[b][lane][0];
+}
+
 // ldmatrix m8n8 b16: matrix j's eight 16-byte rows come from the addresses of lanes 8j..8j+7; thread T gets
 // word T % 4 of row T / 4 of every matrix
 template <int NMAT> inline void ldmatrix(uint32_t addr, uint32_t (&out)[NMAT])
@@ -327,6 +340,7 @@ inline uint32_t fma_bits(uint32_t a, float b, uint32_t c)
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) { return emul::prmt(a, b, s); }
 static inline uint32_t __shfl_sync(uint32_t, uint32_t v, int lane) { return emul::collective(emul::OP_SHFL, v, lane); }
+static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, int mask) { return emul::shfl_xor(v, mask); }
 static inline bool __all_sync(uint32_t, bool p) { return emul::collective(emul::OP_ALL, p) != 0; }
 static inline bool __any_sync(uint32_t, bool p) { return emul::collective(emul::OP_ANY, p) != 0; }
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return emul::collective(emul::OP_ADD, v); }

@@ -205,8 +205,8 @@ extern "C" int emul_run(EmulRequest *rq)
 	uint32_t grid = (uint32_t)std::max(1, rq->ctas);
 	if (grid > P.items)
 		grid = P.items;
-	static uint32_t chunk_counter;
-	chunk_counter = 0;
+	static std::vector<uint32_t> chunk_counters;
+	chunk_counters.assign(std::max<size_t>(1, rq->n_frames), 0u);
 	unsigned threads;
 	if (rq->kernel == 1) {
 		P.items_per_cta = (P.items + grid - 1) / grid;
@@ -215,7 +215,10 @@ extern "C" int emul_run(EmulRequest *rq)
 	} else {
 		uint32_t ch = P.items / (grid * 6u);
 		P.chunk_items = ch < 1u ? 1u : (ch > (uint32_t)kMaxChunkItems ? (uint32_t)kMaxChunkItems : ch);
-		P.chunk_counter = &chunk_counter;
+		P.chunk_counter = chunk_counters.data();
+		P.frame_affine = rq->kernel == 3 && SCOPE_V3_FRAME_AFFINE ? 1u : 0u; // (seeds alternate it off below)
+		if (rq->kernel == 3 && (rq->seed & 4u))
+			P.frame_affine = 0u;
 		threads = (rq->kernel == 3   ? V3::kWarps
 			   : rq->kernel == 2 ? kGroupWarps
 					     : (l.surf ? tma_warps_for<true>(l.src, l.vs) : tma_warps_for<false>(l.src, l.vs))) * 32 + 32;
