@@ -650,25 +650,50 @@ __device__ __forceinline__ void v3_emit_strip(const StripParams &P, uint32_t *wa
 // The same for a strip whose 32 columns all lie inside the frame and whose output rows can be written 16 bytes at a
 // time: a lane takes FOUR neighbouring columns of one level (one 16-byte load per plane, conflict-free: eight lanes
 // cover a level's 128 bytes), a warp four levels per step - 64 steps per strip instead of 256, and an empty group of
-// four levels costs two loads, a vote and one store.  The level's histogram share is summed over the lane's four
-// columns first (B and G still packed: 4 x height <= 65 535, checked by the caller) and then over the eight lanes of
-// the level by three butterfly steps.
+// four levels costs a vote and one store.  A warp's (up to three) steps are loaded up front, so that their latencies
+// overlap.  The level's histogram share is summed over the lane's four columns first (B and G still packed: 8 x
+// height <= 65 535, checked by the caller) and then over the eight lanes of the level by a TRANSPOSING butterfly:
+// after the first exchange the even lanes carry B|G and the odd lanes R, after the second the lanes 0 / 2 / 1 of
+// each eight carry B / G / R - three shuffles instead of nine, and one atomic per level and channel.
 __device__ __forceinline__ void v3_emit_strip_wide(const StripParams &P, uint32_t *wave0, uint32_t frame, uint32_t x_strip,
-						   int warp, int lane)
+						   int warp, int lane_in)
 {
 	constexpr int NW = V3::kWarps;
+	constexpr int kSteps = (64 + NW - 1) / NW;
 	workers_bar<NW>();
+#ifdef SCOPE_EMULATE
+	const int lane = lane_in;
+#else
+	int lane; // (read here: a lane id that ptxas traces back to %tid is re-read with S2R inside the loop)
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+	(void)lane_in;
+#endif
 	uint32_t *hist = P.hist + (size_t)frame * P.hist_stride;
 	const bool do_hist = P.hist_mask != 0u;
 	const int sub = lane >> 3, quad = lane & 7; // level inside the group of four; which four columns
 	uint4 *w4 = reinterpret_cast<uint4 *>(wave0);
 	uint32_t *img = reinterpret_cast<uint32_t *>(P.wave + (size_t)frame * P.wave_stride) + (P.x_offset + x_strip) + 4 * quad;
-	for (int g = warp; g < 64; g += NW) {
+	uint4 a[kSteps], b[kSteps];
+#pragma unroll
+	for (int k = 0; k < kSteps; k++) {
+		const int g = warp + k * NW;
+		if (g < 64) {
+			const int idx = (4 * g + sub) * 8 + quad;
+			a[k] = w4[idx];
+			b[k] = w4[kWaveWords / 4 + idx];
+		} else {
+			a[k] = b[k] = make_uint4(0, 0, 0, 0);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < kSteps; k++) {
+		const int g = warp + k * NW;
+		if (g >= 64)
+			break;
 		const int v = 4 * g + sub;
 		const int idx = v * 8 + quad;
-		const uint4 a = w4[idx], b = w4[kWaveWords / 4 + idx];
 		uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)(255 - v) * P.out_width);
-		const uint32_t any = (a.x | a.y | a.z | a.w) | (b.x | b.y | b.z | b.w);
+		const uint32_t any = (a[k].x | a[k].y | a[k].z | a[k].w) | (b[k].x | b[k].y | b[k].z | b[k].w);
 		if (!__any_sync(0xFFFFFFFFu, any != 0u)) {
 			*dst = make_uint4(0, 0, 0, 0);
 			continue;
@@ -676,31 +701,25 @@ __device__ __forceinline__ void v3_emit_strip_wide(const StripParams &P, uint32_
 		w4[idx] = make_uint4(0, 0, 0, 0);
 		w4[kWaveWords / 4 + idx] = make_uint4(0, 0, 0, 0);
 		uint4 o; // bytes B, G, R, 0 per column
-		o.x = __byte_perm(min_u16x2(a.x, 0x00FF00FFu), min(b.x, 255u), 0x5420);
-		o.y = __byte_perm(min_u16x2(a.y, 0x00FF00FFu), min(b.y, 255u), 0x5420);
-		o.z = __byte_perm(min_u16x2(a.z, 0x00FF00FFu), min(b.z, 255u), 0x5420);
-		o.w = __byte_perm(min_u16x2(a.w, 0x00FF00FFu), min(b.w, 255u), 0x5420);
+		o.x = __byte_perm(min_u16x2(a[k].x, 0x00FF00FFu), min(b[k].x, 255u), 0x5420);
+		o.y = __byte_perm(min_u16x2(a[k].y, 0x00FF00FFu), min(b[k].y, 255u), 0x5420);
+		o.z = __byte_perm(min_u16x2(a[k].z, 0x00FF00FFu), min(b[k].z, 255u), 0x5420);
+		o.w = __byte_perm(min_u16x2(a[k].w, 0x00FF00FFu), min(b[k].w, 255u), 0x5420);
 		*dst = o;
 		if (do_hist) {
-			uint32_t bg = (a.x + a.y) + (a.z + a.w); // two u16 sums side by side
-			uint32_t sr = (b.x + b.y) + (b.z + b.w);
-			bg += __shfl_xor_sync(0xFFFFFFFFu, bg, 1); // (8 x height <= 65 535 as well)
-			sr += __shfl_xor_sync(0xFFFFFFFFu, sr, 1);
-			uint32_t sb = bg & 0xFFFFu, sg = bg >> 16;
-#pragma unroll
-			for (int m = 2; m <= 4; m += 2) {
-				sb += __shfl_xor_sync(0xFFFFFFFFu, sb, m);
-				sg += __shfl_xor_sync(0xFFFFFFFFu, sg, m);
-				sr += __shfl_xor_sync(0xFFFFFFFFu, sr, m);
-			}
-			if (quad == 0) {
-				if (sr)
-					atomicAdd(hist + v * 4 + 0, sr);
-				if (sg)
-					atomicAdd(hist + v * 4 + 1, sg);
-				if (sb)
-					atomicAdd(hist + v * 4 + 2, sb);
-			}
+			const uint32_t bg = (a[k].x + a[k].y) + (a[k].z + a[k].w); // two u16 sums side by side
+			const uint32_t sr = (b[k].x + b[k].y) + (b[k].z + b[k].w);
+			const bool odd = (quad & 1) != 0, up = (quad & 2) != 0;
+			// 1: even lanes collect B|G of the pair, odd lanes R
+			const uint32_t v1 = (odd ? sr : bg) + __shfl_xor_sync(0xFFFFFFFFu, odd ? bg : sr, 1);
+			// 2: of the even lanes, 0 and 4 collect B, 2 and 6 collect G; the odd lanes go on with R
+			const uint32_t lo = v1 & 0xFFFFu, hi = v1 >> 16;
+			const uint32_t keep = odd ? v1 : (up ? hi : lo), give = odd ? v1 : (up ? lo : hi);
+			const uint32_t v2 = keep + __shfl_xor_sync(0xFFFFFFFFu, give, 2);
+			// 3: lanes 0 / 2 / 1 hold B / G / R of the level's 32 columns
+			const uint32_t v3 = v2 + __shfl_xor_sync(0xFFFFFFFFu, v2, 4);
+			if (quad < 3 && v3 != 0u) // histogram.c:379-395: counts in the order R, G, B
+				atomicAdd(hist + v * 4 + (quad == 0 ? 2 : (quad == 2 ? 1 : 0)), v3);
 		}
 	}
 	workers_bar<NW>();
