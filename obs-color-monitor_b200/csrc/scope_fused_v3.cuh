@@ -64,6 +64,10 @@ namespace scope {
 #ifndef SCOPE_V3_FRAME_AFFINE
 #define SCOPE_V3_FRAME_AFFINE 1 // strips are claimed frame by frame (StripParams::frame_affine; 0: one counter over the batch)
 #endif
+#ifndef SCOPE_V3_DIAG
+#define SCOPE_V3_DIAG 0 // diagnostic builds (never shipped, results wrong by construction): bit 0 no end-of-strip write-out
+                        // (its two barriers stay), bit 1 not even the barriers, bit 2 no vectorscope flush
+#endif
 #ifndef SCOPE_V3_LEAN
 #define SCOPE_V3_LEAN 1 // visits that lie inside the frame and have a successor run without the per-visit checks (0: A/B partner)
 #endif
@@ -1050,7 +1054,7 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 		const uint32_t last = first + count;
 		for (uint32_t item = first; item < last; item++) {
 			const uint32_t frame = item / P.strips, strip = item - frame * P.strips;
-			if (frame != cur_frame && cur_frame != 0xFFFFFFFFu)
+			if (frame != cur_frame && cur_frame != 0xFFFFFFFFu && !(SCOPE_V3_DIAG & 4))
 				v3_flush(P, vs, cur_frame, tid);
 			cur_frame = frame;
 			const uint32_t x = strip * kStripPx + lane;
@@ -1105,6 +1109,13 @@ __device__ __forceinline__ void v3_consume(const StripParams &P, uint8_t *smem, 
 			}
 			v3_resolve(pend);
 			v3_pend_clear(pend);
+#if SCOPE_V3_DIAG & 3
+			if (!(SCOPE_V3_DIAG & 2)) {
+				workers_bar<V3::kWarps>();
+				workers_bar<V3::kWarps>();
+			}
+			continue;
+#endif
 #if SCOPE_V3_WIDE_EMIT
 			// (from the launch parameters alone, every time: nothing to keep in a register across the strip)
 			// 16-byte stores into the waveform rows, packed u16 sums of eight columns

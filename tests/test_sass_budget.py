@@ -49,6 +49,38 @@ def test_headline_kernel_resources_and_instruction_forms():
 
 
 @needs_tools
+def test_headline_kernel_lean_visit_budget():
+    """the visit of the lean loop (blocks inside the frame that have a successor): from the tile wait in front of the
+    second ldmatrix of the kernel to the branch behind the sixteen shared-memory atomics of the ordinary block.
+    Round 2 took it from 143 to ~118 instructions: no range checks, the stage handed back with ONE LOP3 and an arrive
+    whose barrier offset is an immediate, no state of the previous visit's vectorscope adds, and the register constants
+    read once from shared memory - ptxas re-materialises what it can trace to the constant bank with an LDC per visit."""
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    body = sass[sass.index(V3):]
+    body = body[:body.index("Function :", 10)] if "Function :" in body[10:] else body
+    ins = [m.group(1) for m in re.finditer(r"/\*[0-9a-f]{4,5}\*/\s+(.*?)\s*;", body)]
+    ldsm = [i for i, t in enumerate(ins) if "LDSM" in t]
+    assert len(ldsm) >= 4
+    i = ldsm[1]
+    j = i
+    while "SYNCS.PHASECHK" not in ins[j]:
+        j -= 1
+    k, atoms = i + 1, 0
+    while atoms < 16:
+        atoms += "ATOMS" in ins[k]
+        k += 1
+    while not ins[k].startswith("BRA") and "BRA" not in ins[k].split()[0:2]:
+        k += 1
+    visit = ins[j - 1:k + 1]
+    assert len(visit) <= 126, len(visit)
+    assert sum(("LDC" in t) for t in visit) <= 2, [t for t in visit if "LDC" in t]
+    assert not any("LDL" in t or "STL" in t for t in visit), "spill inside the visit"
+    arrives = [t for t in visit if "SYNCS.ARRIVE" in t]
+    assert len(arrives) == 1 and re.search(r"\+0x[0-9a-f]+\]", arrives[0]), arrives   # barrier offset as an immediate
+    assert sum("VOTE" in t for t in visit) == 1
+
+
+@needs_tools
 def test_general_fused_loop_budget():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_budget.py"), LIB, "--kernel", GENERAL],
                          capture_output=True, text=True, check=True).stdout
