@@ -95,6 +95,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout: float = 4.0):
+        """block until nvidia-smi has delivered its first sample (its start-up can take longer than a whole timed
+        region), then forget what was sampled so far: everything kept from here on is taken while the caller keeps
+        the GPU busy"""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.01)
+        self.mark = len(self.lines)
+
+    def n_samples(self):
+        return len(self.lines) - getattr(self, "mark", 0)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -105,7 +117,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "mark", 0):]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -376,10 +388,21 @@ def run_b200_arm(args):
     # batch, bit for bit against the reference's own compiled loops (oracle/_ref; the oracle port if absent)
     parity = check_parity(args, pkg, batch, out, st, n_check=min(4, n)) if rank == 0 else None
 
+    # clocks DURING load: the sampler starts, then the same steps run untimed until it has seen the GPU busy for a
+    # while (>= 0.3 s and >= 5 samples on rank 0; the other ranks keep their GPUs equally busy for the same time), and
+    # the timed steps follow without a gap
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first()
+    t_load = time.time()
+    while True:
+        for _ in range(8):
+            step()
+        torch.cuda.synchronize()
+        dt_load = time.time() - t_load
+        if dt_load >= 0.3 and (rank != 0 or sampler.n_samples() >= 5 or dt_load >= 3.0):
+            break
     eng.ctx.profile_enable(True)
     eng.ctx.profile_read()
     launches0 = eng.launch_count
@@ -846,10 +869,23 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
     eng.ctx.profile_enable(False)
     kernel_us = 1e3 * sorted(kms)[len(kms) // 2] if kms else None
 
+    # clocks DURING load: every frame has a cross-rank barrier inside, so all ranks run the SAME number of untimed
+    # frames under the sampler (about 0.4 s worth, from rank 0's own estimate), then the timed ones without a gap
     sampler = ClockSampler(dev.index if dev.index is not None else 0)
     if rank == 0:
         sampler.start()
-        time.sleep(0.2)
+        sampler.wait_first()
+    t_est = time.time()
+    for i in range(G if use_graph else 8):
+        step(i)
+    barrier()
+    per_frame = max((time.time() - t_est) / (G if use_graph else 8), 5e-6)
+    n_load = torch.tensor([min(int(0.4 / per_frame), 40000)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(n_load, src=0)
+    n_load = max(int(n_load.item()) // G * G, G)
+    for i in range(n_load):
+        step(i)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     join = torch.cuda.Event()
     l0 = eng.launch_count
@@ -894,7 +930,7 @@ def measure_config4(eng, pkg, dev, world, rank, bands="rows", reduce="peers", gr
         "gpu_launches_per_frame": launches_per_frame if launches_per_frame is not None else (eng.launch_count - l0) / steps,
         "achieved_read_GBps_all_ranks": steps * W * H * 4 / (ms * 1e-3) / 1e9, "clocks": clocks, "parity": parity,
         "roofline": {"bound": "hbm", "unit": "GB/s", "note": "per rank: its band's pixel bytes / the frame time",
-                     "achieved": steps * W * H * 4 / world / (ms * 1e-3) / 1e9},
+                     "achieved": steps * W * H * 4 / (emulate or world) / (ms * 1e-3) / 1e9},
     }
 
 
@@ -967,6 +1003,7 @@ def run_stream_vscope(args):
     n = 60 * max(args.steps, 1)
     sampler = ClockSampler(0)
     sampler.start()
+    sampler.wait_first()
     eng.ctx.profile_enable(True)
     eng.ctx.profile_read()
     t0 = time.perf_counter()

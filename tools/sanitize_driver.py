@@ -32,6 +32,16 @@ def main():
                 if "vscope" in res:
                     assert np.array_equal(res["vscope"], orc.vectorscope(yuv))
                 n += 1
+    # tall frames: seven tiles per strip, so that scope_fused_kernel_v3 runs its lean visits (blocks inside the frame
+    # with a successor), the 16-byte write-out and, on the solid frame, the flat-block and take-back paths inside them
+    tall = [fr.random(96, 700, seed=6), fr.solid(64, 700, (200, 17, 90, 255)), fr.alpha_stripes(72, 650, seed=7)]
+    for f in tall:
+        yuv = orc.rgb_to_yuv(f, 2)
+        res = eng.accumulate_host(f, settings=pkg.ScopeSettings(scopes=7, mode=pkg.MODE_FUSED))
+        assert np.array_equal(res["hist"], orc.histogram_counts(0x07, f, yuv))
+        assert np.array_equal(res["wave"], orc.waveform(0x07, f, yuv))
+        assert np.array_equal(res["vscope"], orc.vectorscope(yuv))
+        n += 1
     # pitched plane whose rows are not 16-byte multiples (plain-load kernel), ring slots
     odd = fr.random(75, 40, seed=5)
     res = eng.accumulate_host(odd)
