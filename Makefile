@@ -42,7 +42,7 @@ clean:
 #   v3_red         DIAGNOSTIC: vectorscope adds without return value (saturation of flat content then wrong)
 #   w8, straight, nopipe: build flags of the general kernel that tests/test_kernel_emulation.py still covers
 VARIANT = $(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/scope_ffi.cu -Xlinker --version-script=$(PKG)/csrc/exports.map
-VARIANTS = v3_base v3_lean_defer v3_lean_ldc v3_lean_w24 v3_lean_narrow v3_noaffine v3_pf12 v3_pf20 v3_pf3 v3_d1 v3_d2 v3_d4 v3_d6 v3_w23s4 v3_w25s3 v3_w26s3 v3_w27pf0 v3off v3_scalar v3_pf0 v3_nop v3_noload v3_s1 v3_s2 v3_s3 v3_red w8 straight nopipe
+VARIANTS = v3_base v3_lean_defer v3_lean_ldc v3_lean_w24 v3_lean_narrow v3_noaffine v3_nobg v3_pf12 v3_pf20 v3_pf3 v3_d1 v3_d2 v3_d4 v3_d6 v3_w23s4 v3_w25s3 v3_w26s3 v3_w27pf0 v3off v3_scalar v3_pf0 v3_nop v3_noload v3_s1 v3_s2 v3_s3 v3_red w8 straight nopipe
 FLAGS_v3off = -DSCOPE_V3=0
 FLAGS_v3_base = -DSCOPE_V3_LEAN=0 -DSCOPE_V3_RESOLVE_NOW=0 -DSCOPE_V3_SMEM_CONSTS=0
 FLAGS_v3_lean_defer = -DSCOPE_V3_RESOLVE_NOW=0
@@ -50,6 +50,7 @@ FLAGS_v3_lean_w24 = -DSCOPE_V3_WARPS=24
 FLAGS_v3_lean_ldc = -DSCOPE_V3_SMEM_CONSTS=0
 FLAGS_v3_lean_narrow = -DSCOPE_V3_WIDE_EMIT=0
 FLAGS_v3_noaffine = -DSCOPE_V3_FRAME_AFFINE=0
+FLAGS_v3_nobg = -DSCOPE_V3_BG_SKIP=0
 FLAGS_v3_pf3 = -DSCOPE_V3_L2_AHEAD=3
 FLAGS_v3_d1 = -DSCOPE_V3_DIAG=1
 FLAGS_v3_d2 = -DSCOPE_V3_DIAG=2

@@ -442,7 +442,10 @@ def run_b200_arm(args):
         pass
     achieved = alg_bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "scope_strip_kernel_tma, the fused strip kernel (scopes: %s)" % args.scopes,
+                "traffic": None,
+                "kernel": ("scope_fused_kernel_v3 (hist RGB + waveform RGB + vectorscope in one pass)"
+                           if sorted(args.scopes.split(",")) == ["hist", "vscope", "wave"]
+                           else "scope_strip_kernel_tma, the general strip kernel (scopes: %s)" % args.scopes),
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
                 "kernel_share_of_step": (k_ms * launches_per_step) / (elapsed_ms / args.steps)}
     try:

@@ -68,6 +68,10 @@ namespace scope {
 #define SCOPE_V3_DIAG 0 // diagnostic builds (never shipped, results wrong by construction): bit 0 no end-of-strip write-out
                         // (its two barriers stay), bit 1 not even the barriers, bit 2 no vectorscope flush
 #endif
+#ifndef SCOPE_V3_BG_SKIP
+#define SCOPE_V3_BG_SKIP 1 // blocks with lanes whose four pixels are equal (screen content: text on a flat background) go through
+                           // v3_block_mixed: the lanes that hold the background colour leave their vectorscope adds to ONE lane
+#endif
 #ifndef SCOPE_V3_LEAN
 #define SCOPE_V3_LEAN 1 // visits that lie inside the frame and have a successor run without the per-visit checks (0: A/B partner)
 #endif
@@ -440,9 +444,11 @@ __device__ __forceinline__ void v3_block_fast(const uint32_t (&p)[4], const V3Co
 
 // the same block with the vectorscope adds in front: their old values have arrived by the time the column-bin adds
 // have been issued, so the take-back needs no state that outlives the block
-template <int CS>
+// MIXED (cold paths only): lanes with `bg` leave out their vectorscope adds, and a lane with lead_count != 0 adds that
+// many to the bin of its first pixel at the end (see v3_block_mixed)
+template <int CS, bool MIXED = false>
 __device__ __forceinline__ void v3_block_fast_now(const uint32_t (&p)[4], const V3Consts &k, uint32_t ku, uint32_t kv,
-						  uint32_t zero_reg)
+						  uint32_t zero_reg, bool bg = false, uint32_t lead_count = 0u)
 {
 	V3Px px[4];
 #pragma unroll
@@ -457,6 +463,10 @@ __device__ __forceinline__ void v3_block_fast_now(const uint32_t (&p)[4], const 
 		if (SCOPE_V3_SKIP & 2) {
 			v3_keep(q.addr[i], q.add[i]);
 			q.old[i] = 0;
+		} else if (MIXED) {
+			q.old[i] = 0u;
+			if (!bg)
+				q.old[i] = atom_shared_add(q.addr[i], q.add[i]);
 		} else {
 			q.old[i] = atom_shared_add(q.addr[i], q.add[i]);
 		}
@@ -487,6 +497,11 @@ __device__ __forceinline__ void v3_block_fast_now(const uint32_t (&p)[4], const 
 		}
 	}
 	v3_resolve(q);
+	if (MIXED && lead_count != 0u) { // the flat block's rule (v3_block_flat): an add that finds its half at >= 0x8000 is undone
+		const uint32_t old = atom_shared_add(q.addr[0], q.add[0] * lead_count);
+		if (old & (q.add[0] << 15))
+			red_shared(q.addr[0], 0u - q.add[0] * lead_count);
+	}
 }
 
 template <int CS>
@@ -521,6 +536,53 @@ __device__ __forceinline__ void v3_block_flat(uint32_t p0, const V3Consts &k, ui
 		if (old & (add << 15))
 			red_shared(addr, 0u - add * 128u);
 	}
+}
+
+// a consumer warp's standing state (used from here on)
+struct V3Warp {
+	V3Consts k;
+	uint32_t ku, kv, zero;
+	uint32_t rows_base; // this lane's ldmatrix address inside stage 0
+	uint32_t base;      // the CTA's shared-memory window
+	uint32_t bar_full, bar_empty;
+	uint32_t y_warp;
+	int lane;
+};
+
+// An opaque block inside the frame in which SOME lanes hold four equal pixels but not all lanes the same one: screen
+// content - text, window edges - on a flat background.  Left to the ordinary block, most of the 32 lanes of every
+// vectorscope add would sit on the background's word and be served one after the other (32-way: 16 % of the HBM peak
+// on `--content ui`).  Here the background is the colour of the first such lane; the lanes that hold nothing else
+// (`bg`) skip their four vectorscope adds and that first lane adds 4 x their number at once, with the flat block's
+// take-back rule.  Everything else is the ordinary block - the SAME copy of it (v3_block_fast_now<CS, true>): with
+// fewer than eight such lanes no lane is `bg` and the call is the ordinary block.  (Two earlier forms cost the
+// headline more than screen content gained, profiles/r02/c39 and c40: one out-of-line copy per kernel, `__noinline__`
+// - the call's ABI took 3 % off every content and 10 % off solid frames; a second inlined block per cold path - 1.5 %
+// off the mixed batch through code size alone, although picture-like content never enters it.)
+template <int CS>
+__device__ __forceinline__ void v3_block_mixed(const uint32_t (&p)[4], bool flat, const V3Warp &w)
+{
+	bool bg = false;
+	uint32_t lead_count = 0u;
+#if SCOPE_V3_BG_SKIP
+	const uint32_t fm = __ballot_sync(0xFFFFFFFFu, flat);
+	if (__popc(fm) >= 8) {
+		const int leader = __ffs((int)fm) - 1;
+		const uint32_t key = __shfl_sync(0xFFFFFFFFu, p[0], leader);
+		bg = flat && p[0] == key;
+		const uint32_t n_bg = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, bg));
+#ifdef SCOPE_EMULATE
+		const int lane = w.lane;
+#else
+		int lane; // (read where it is needed: a longer life of w.lane costs the visits' loop six instructions)
+		asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+#endif
+		lead_count = lane == leader ? 4u * n_bg : 0u;
+	}
+#else
+	(void)flat;
+#endif
+	v3_block_fast_now<CS, true>(p, w.k, w.ku, w.kv, w.zero, bg, lead_count);
 }
 
 // rows partly outside the frame, columns outside it, transparent pixels: per-pixel conditions
@@ -832,15 +894,6 @@ __device__ __forceinline__ void v3_produce(const StripParams &P, const CUtensorM
 // ---------------------------------------------------------------------------
 // consumer warps
 // ---------------------------------------------------------------------------
-struct V3Warp {
-	V3Consts k;
-	uint32_t ku, kv, zero;
-	uint32_t rows_base; // this lane's ldmatrix address inside stage 0
-	uint32_t base;      // the CTA's shared-memory window
-	uint32_t bar_full, bar_empty;
-	uint32_t y_warp;
-	int lane;
-};
 
 // wait for the tile in stage S and read this warp's four rows of it
 template <int S>
@@ -908,7 +961,11 @@ __device__ __forceinline__ void v3_visit(const StripParams &P, const V3Warp &w, 
 			if (__all_sync(0xFFFFFFFFu, ((m_and ^ m_or) | (p[0] ^ p_lane0)) == 0u))
 				v3_block_flat<CS>(p[0], w.k, w.ku, w.kv, w.zero, w.lane);
 			else
+#if SCOPE_V3_RESOLVE_NOW
+				v3_block_mixed<CS>(p, m_and == m_or, w);
+#else
 				v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+#endif
 			done = true;
 		}
 		if (!done) {
@@ -975,7 +1032,11 @@ __device__ __forceinline__ void v3_visit_lean(const V3Warp &w, V3Phase &ph, cons
 			if (__all_sync(0xFFFFFFFFu, ((m_and ^ m_or) | (p[0] ^ p_lane0)) == 0u))
 				v3_block_flat<CS>(p[0], w.k, w.ku, w.kv, w.zero, w.lane);
 			else
+#if SCOPE_V3_RESOLVE_NOW
+				v3_block_mixed<CS>(p, m_and == m_or, w);
+#else
 				v3_block_ordinary<CS>(p, w.k, w.ku, w.kv, w.zero, pend);
+#endif
 		} else {
 			v3_block_slow<CS>(p, w.k, w.ku, w.kv, w.zero, true, 0xFu);
 		}

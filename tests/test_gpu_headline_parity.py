@@ -124,3 +124,30 @@ def _cols(d, x0, x1):
     off = x0 * 4
     n = (H - 1) * W * 4 + (W - x0) * 4
     return torch.as_strided(flat[off:off + n], (H, (W - x0) * 4), (W * 4, 1))
+
+
+def test_screen_content_and_background_lanes_vs_oracle(engine, oracle, pkg):
+    """scope_fused_kernel_v3's v3_block_mixed (lanes that hold four equal pixels leave their vectorscope adds to one
+    lane): a 4K screen-like frame (text on a flat background; its background bin saturates), and a random frame with
+    small flat patches whose bins stay far below 255, so that a wrong count of background lanes would show"""
+    import torch
+    ui = _batch(2, 3840, 2160, "ui")
+    out = engine.accumulate_device(ui)
+    torch.cuda.synchronize()
+    host = ui.cpu().numpy()
+    for i in range(2):
+        _compare_device(out, i, _expect_all(oracle, host[i]), f"4K ui frame {i}")
+    f = pkg.frames.random(256, 1400, seed=123)
+    f[..., 3] = 255
+    rng = np.random.default_rng(5)
+    for k in range(60):
+        y0 = 4 * int(rng.integers(0, 1400 // 4))
+        x0 = int(rng.integers(0, 256 - 32))
+        n = int(rng.integers(5, 32))
+        f[y0:y0 + 4, x0:x0 + n] = (int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 256)), 255)
+    d = torch.from_numpy(np.ascontiguousarray(f[None])).cuda()
+    out = engine.accumulate_device(d)
+    torch.cuda.synchronize()
+    exp = _expect_all(oracle, f)
+    assert exp[2].max() < 255
+    _compare_device(out, 0, exp, "random frame with flat patches")

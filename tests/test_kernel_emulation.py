@@ -366,6 +366,34 @@ def test_v3_saturation_flat_and_almost_flat(emul_libs, oracle, pkg):
         check(oracle, ui, out, yuv, 0x07, 0x07, True, f"v3 ui seed {seed}")
 
 
+def test_v3_background_lanes(emul_libs, oracle, pkg):
+    """v3_block_mixed: blocks in which 8 or more lanes hold four equal pixels (text on a flat background).  The patches
+    are small enough that their vectorscope bins stay far below 255 - a wrong count of background lanes shows (on
+    screen-like frames every such bin saturates and hides it): 12 lanes of one colour, 31 lanes, 7 lanes (below the
+    threshold: ordinary block), flat lanes of two colours (only the first lane's colour is the background), a flat
+    patch with transparent pixels (per-pixel path), inside the lean loop (tall frame) and in a strip's last tiles."""
+    lib = emul_libs["default"]
+    f = pkg.frames.random(64, 700, seed=77)
+    f[..., 3] = 255
+
+    def patch(y0, x0, n, colour):
+        f[y0:y0 + 4, x0:x0 + n] = colour
+    patch(8, 10, 12, (200, 10, 60, 255))
+    patch(116, 33, 31, (12, 240, 99, 255))
+    patch(224, 3, 7, (77, 77, 200, 255))
+    patch(332, 0, 10, (5, 130, 250, 255))
+    patch(332, 12, 9, (250, 130, 5, 255))
+    patch(440, 40, 16, (90, 90, 90, 255))
+    f[441, 44, 3] = 0
+    patch(692, 2, 20, (33, 66, 99, 255))          # rows 692..695: the strip's last (partial) tile
+    frames = np.ascontiguousarray(f[None])
+    yuv = [oracle.rgb_to_yuv(frames[0], 2)]
+    for seed, land in ((41, 30), (42, 3)):
+        out = run(lib, frames, kernel=K_V3, seed=seed, land=land, ctas=2)
+        check(oracle, frames, out, yuv, 0x07, 0x07, True, f"v3 background lanes seed {seed}")
+    assert out[2][0].max() < 255
+
+
 def test_v3_extreme_geometries(emul_libs, oracle, pkg):
     """one row, one tile exactly (23 warps x 4 rows = 92), one row more, fewer rows than one warp takes, narrow strips"""
     lib = emul_libs["default"]

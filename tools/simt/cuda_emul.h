@@ -27,6 +27,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __restrict__
@@ -346,6 +347,7 @@ static inline bool __any_sync(uint32_t, bool p) { return emul::collective(emul::
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) { return emul::collective(emul::OP_ADD, v); }
 static inline uint32_t __ballot_sync(uint32_t, bool p) { return emul::collective(emul::OP_BALLOT, p); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline void __syncwarp() { emul::collective(emul::OP_SYNC, 0); }
 static inline void __syncthreads() { emul::bar_sync(0, (int)emul::W->cur->cta->block_dim); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v)
