@@ -34,7 +34,12 @@ def main():
                 n += 1
     # tall frames: seven tiles per strip, so that scope_fused_kernel_v3 runs its lean visits (blocks inside the frame
     # with a successor), the 16-byte write-out and, on the solid frame, the flat-block and take-back paths inside them
-    tall = [fr.random(96, 700, seed=6), fr.solid(64, 700, (200, 17, 90, 255)), fr.alpha_stripes(72, 650, seed=7)]
+    patched = fr.random(64, 700, seed=8)          # flat patches: lanes with four equal pixels (background-lane rule)
+    patched[..., 3] = 255
+    patched[8:12, 10:22] = (200, 10, 60, 255)
+    patched[332:336, 0:31] = (5, 130, 250, 255)
+    tall = [fr.random(96, 700, seed=6), fr.solid(64, 700, (200, 17, 90, 255)), fr.alpha_stripes(72, 650, seed=7),
+            fr.ui(96, 700, 1), patched]
     for f in tall:
         yuv = orc.rgb_to_yuv(f, 2)
         res = eng.accumulate_host(f, settings=pkg.ScopeSettings(scopes=7, mode=pkg.MODE_FUSED))
