@@ -366,6 +366,23 @@ def test_v3_saturation_flat_and_almost_flat(emul_libs, oracle, pkg):
         check(oracle, ui, out, yuv, 0x07, 0x07, True, f"v3 ui seed {seed}")
 
 
+def test_v3_frame_affine_claiming(emul_libs, oracle, pkg):
+    """one work counter per frame (StripParams::frame_affine): more CTAs than frames, more frames than CTAs, one frame,
+    chunk sizes 1 and > 1 - every strip of every frame exactly once, whatever order the CTAs come in (seeds without
+    bit 2 run the per-frame counters, the emulator's launcher turns them off for the others)"""
+    lib = emul_libs["default"]
+    fr = pkg.frames
+    for n_frames, w, h, ctas, seeds in ((2, 100, 120, 5, (1, 2, 8)), (7, 40, 110, 2, (3, 16)), (1, 130, 109, 3, (9,)),
+                                        (12, 64, 40, 3, (10, 17)),
+                                        (2, 1024, 8, 3, (1, 8))):       # many strips per frame: guided chunks > 1
+        frames = np.stack([fr.random(w, h, 50 + i) if i % 2 else fr.natural(w, h, 60 + i) for i in range(n_frames)])
+        yuv = [oracle.rgb_to_yuv(f, 2) for f in frames]
+        for seed in seeds:
+            assert not seed & 4
+            out = run(lib, frames, kernel=K_V3, seed=seed, land=30, ctas=ctas)
+            check(oracle, frames, out, yuv, 0x07, 0x07, True, f"v3 affine {n_frames} frames, {ctas} CTAs, seed {seed}")
+
+
 def test_v3_background_lanes(emul_libs, oracle, pkg):
     """v3_block_mixed: blocks in which 8 or more lanes hold four equal pixels (text on a flat background).  The patches
     are small enough that their vectorscope bins stay far below 255 - a wrong count of background lanes shows (on
