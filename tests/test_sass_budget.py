@@ -75,7 +75,7 @@ def test_headline_kernel_lean_visit_budget():
     while not ins[k].startswith("BRA") and "BRA" not in ins[k].split()[0:2]:
         k += 1
     visit = ins[j - 1:k + 1]
-    assert len(visit) <= 126, len(visit)
+    assert len(visit) <= 130, len(visit)   # 125 / 118 / 116 for the three unrolled visits of the shipped build
     assert sum(("LDC" in t) for t in visit) <= 2, [t for t in visit if "LDC" in t]
     assert not any("LDL" in t or "STL" in t for t in visit), "spill inside the visit"
     arrives = [t for t in visit if "SYNCS.ARRIVE" in t]
